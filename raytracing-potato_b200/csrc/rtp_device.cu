@@ -1,0 +1,1165 @@
+// rtp_device.cu — sm_100a kernels and the device-facing half of the C ABI.
+//
+// Arithmetic contract: every expression below that restates a reference expression keeps the
+// reference's association order, and this file is compiled with --fmad=false, so no multiply-add
+// is contracted (rustc never fuses). f64 division and sqrt are IEEE-correct in CUDA. The only
+// operations that may differ from the CPU by an ulp are atan2/asin (sphere and sky uv).
+//
+// Reference citations are file:line under /root/reference/src.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rtp_internal.h"
+
+namespace rtp {
+
+#define RTP_CUDA(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return set_error(RTP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+constexpr double kRayEpsilon = 1e-3;  // utility.rs:30
+constexpr double kSmol = 1e-7;        // utility.rs:31
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTau = 6.28318530717958647692528676655900577;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ D3 mk(double x, double y, double z) { return D3{x, y, z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ D3 cmul(D3 a, D3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+// nalgebra 0.29 reductions on static 3-vectors
+__device__ __forceinline__ double dot(D3 a, D3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ double norm_squared(D3 a) { return 0.0 + dot(a, a); }
+__device__ __forceinline__ double norm(D3 a) { return sqrt(norm_squared(a)); }
+__device__ __forceinline__ D3 normalize(D3 a) {
+    const double n = norm(a);
+    return mk(a.x / n, a.y / n, a.z / n);
+}
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+struct Counters {
+    unsigned long long rays, paths, node_visits, triangle_tests, sphere_tests;
+};
+
+struct LocalCounters {
+    unsigned int rays, node_visits, triangle_tests, sphere_tests;
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1: closest hit. Restates bvh.rs:93-124 as a stack-free pre-order walk (see rtp_internal.h).
+// ---------------------------------------------------------------------------------------------
+
+struct HitRec {
+    double t;       // in: ray.t_max, out: t of the closest hit (unchanged on miss)
+    double u, v;    // triangle barycentrics of the winner
+    uint32_t slot;  // primitive slot of the winner, kNoPrim on miss
+    uint32_t kind;  // rtp_hittable_kind of the winner
+};
+
+// utility.rs:137-154 AABB::collide — literal form (12 minNum/maxNum)
+__device__ __forceinline__ bool collide_literal(const double2 b0, const double2 b1, const double2 b2, D3 o, D3 inv, double ray_tmin,
+                                                double ray_tmax) {
+    // b0 = (min.x, min.y), b1 = (min.z, max.x), b2 = (max.y, max.z)
+    const double t0x = (b0.x - o.x) * inv.x, t0y = (b0.y - o.y) * inv.y, t0z = (b1.x - o.z) * inv.z;
+    const double t1x = (b1.y - o.x) * inv.x, t1y = (b2.x - o.y) * inv.y, t1z = (b2.y - o.z) * inv.z;
+    const double t_min = fmax(fmax(fmax(ray_tmin, fmin(t0x, t1x)), fmin(t0y, t1y)), fmin(t0z, t1z));
+    const double t_max = fmin(fmin(fmin(ray_tmax, fmax(t0x, t1x)), fmax(t0y, t1y)), fmax(t0z, t1z));
+    return t_max >= t_min;
+}
+
+// hittable.rs:65-108 hit_triangle up to the accept test
+__device__ __forceinline__ bool test_triangle(const DPrim* __restrict__ p, D3 o, D3 d, double ray_tmin, double ray_tmax, double& t_out,
+                                              double& u_out, double& v_out) {
+    const double* pd = reinterpret_cast<const double*>(p);  // a[3] ba[3] ca[3] are contiguous
+    const double2 q0 = ldg2(pd), q1 = ldg2(pd + 2), q2 = ldg2(pd + 4), q3 = ldg2(pd + 6);
+    const double q4 = __ldg(pd + 8);
+    const D3 a = mk(q0.x, q0.y, q1.x);
+    const D3 ba = mk(q1.y, q2.x, q2.y);
+    const D3 ca = mk(q3.x, q3.y, q4);
+    const D3 pa = a - o;
+
+    const double det = ba.x * ca.y * d.z + ba.y * ca.z * d.x + ba.z * ca.x * d.y - ba.x * ca.z * d.y - ba.y * ca.x * d.z -
+                       ba.z * ca.y * d.x;
+    if (fabs(det) < kSmol) return false;
+    const double inv_det = 1.0 / det;
+
+    const double t = (pa.x * (ba.y * ca.z - ba.z * ca.y) + pa.y * (ba.z * ca.x - ba.x * ca.z) + pa.z * (ba.x * ca.y - ba.y * ca.x)) * inv_det;
+    const double u = (pa.x * (ca.y * d.z - ca.z * d.y) + pa.y * (ca.z * d.x - ca.x * d.z) + pa.z * (ca.x * d.y - ca.y * d.x)) * inv_det;
+    const double v = (pa.x * (ba.z * d.y - ba.y * d.z) + pa.y * (ba.x * d.z - ba.z * d.x) + pa.z * (ba.y * d.x - ba.x * d.y)) * inv_det;
+    const double w = 1.0 - u - v;
+    if (t < ray_tmin || t > ray_tmax || u < 0.0 || v < 0.0 || w < 0.0) return false;
+    t_out = t; u_out = u; v_out = v;
+    return true;
+}
+
+// hittable.rs:39-57 hit_sphere up to the accepted root
+__device__ __forceinline__ bool test_sphere(const DPrim* __restrict__ p, D3 o, D3 d, double ray_tmin, double ray_tmax, double& t_out) {
+    const double* pd = reinterpret_cast<const double*>(p);  // center in a[], radius in ba[0]
+    const double2 q0 = ldg2(pd), q1 = ldg2(pd + 2);
+    const D3 center = mk(q0.x, q0.y, q1.x);
+    const double radius = q1.y;
+    const D3 to_center = o - center;
+    const double a = norm_squared(d);
+    const double half_b = dot(d, to_center);
+    const double c = norm_squared(to_center) - radius * radius;
+    const double delta = half_b * half_b - a * c;
+    if (delta <= 0.0) return false;
+    const double sqrt_delta = sqrt(delta);
+    double t = (-half_b - sqrt_delta) / a;
+    if (t < ray_tmin || t > ray_tmax) {
+        t = (-half_b + sqrt_delta) / a;
+        if (t < ray_tmin || t > ray_tmax) return false;
+    }
+    t_out = t;
+    return true;
+}
+
+// bvh.rs:121-124 Bvh::hit. `h.t` carries ray.t_max in and the closest t out.
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit_bvh(const DSceneView& sc, D3 o, D3 d, double ray_tmin, HitRec& h, LocalCounters& lc) {
+    const D3 inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
+    const DNode* __restrict__ nodes = sc.nodes;
+    const uint32_t n_nodes = sc.n_nodes;
+    uint32_t node = 0;
+    h.slot = kNoPrim;
+    for (;;) {
+        // walk until a leaf passes its own slab gate (bvh.rs:96, 103) or the tree is exhausted
+        uint32_t prim = kNoPrim, kind = 0;
+        while (node < n_nodes) {
+            const double* nb = nodes[node].bmin;
+            const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
+            const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
+            if (COUNT) lc.node_visits++;
+            if (collide_literal(b0, b1, b2, o, inv, ray_tmin, h.t)) {
+                node = node + 1;
+                if (meta.y != kNoPrim) { prim = meta.y; kind = meta.z; break; }
+            } else {
+                node = meta.x;
+            }
+        }
+        if (prim == kNoPrim) break;
+        const DPrim* p = sc.prims + prim;
+        double t, u = 0.0, v = 0.0;
+        bool hit;
+        if (kind == RTP_HITTABLE_TRIANGLE) {
+            if (COUNT) lc.triangle_tests++;
+            hit = test_triangle(p, o, d, ray_tmin, h.t, t, u, v);
+        } else {
+            if (COUNT) lc.sphere_tests++;
+            hit = test_sphere(p, o, d, ray_tmin, h.t, t);
+        }
+        if (hit) {  // bvh.rs:107-111: shrink t_max, later hit replaces
+            h.t = t; h.u = u; h.v = v; h.slot = prim; h.kind = kind;
+        }
+    }
+}
+
+// hittable.rs:110-120 hit_list over the primitive list in caller order
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit_list(const DSceneView& sc, D3 o, D3 d, double ray_tmin, HitRec& h, LocalCounters& lc) {
+    h.slot = kNoPrim;
+    for (uint32_t slot = 0; slot < sc.n_prims; ++slot) {
+        const uint32_t kind = __ldg(&sc.nodes[slot].kind);
+        const DPrim* p = sc.prims + slot;
+        double t, u = 0.0, v = 0.0;
+        bool hit;
+        if (kind == RTP_HITTABLE_TRIANGLE) {
+            if (COUNT) lc.triangle_tests++;
+            hit = test_triangle(p, o, d, ray_tmin, h.t, t, u, v);
+        } else {
+            if (COUNT) lc.sphere_tests++;
+            hit = test_sphere(p, o, d, ray_tmin, h.t, t);
+        }
+        if (hit) { h.t = t; h.u = u; h.v = v; h.slot = slot; h.kind = kind; }
+    }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void closest_hit(const DSceneView& sc, D3 o, D3 d, double ray_tmin, HitRec& h, LocalCounters& lc) {
+    lc.rays++;
+    if (sc.root_kind == RTP_ROOT_BVH) closest_hit_bvh<COUNT>(sc, o, d, ray_tmin, h, lc);
+    else closest_hit_list<COUNT>(sc, o, d, ray_tmin, h, lc);
+}
+
+// The rest of `Hit` for the winner (hittable.rs:58-62, 102-107). Pure function of (ray, t, u, v,
+// primitive), so evaluating it once after traversal gives the bits the reference computed at accept time.
+struct Surface {
+    D3 position, normal;
+    double u, v;
+    uint32_t material, leaf;
+};
+
+__device__ __forceinline__ void finish_hit(const DSceneView& sc, D3 o, D3 d, const HitRec& h, Surface& s) {
+    const DPrim* p = sc.prims + h.slot;
+    s.leaf = __ldg(&p->leaf);
+    s.material = __ldg(&p->material);
+    s.position = o + h.t * d;  // utility.rs:67-69 Ray::at
+}
+
+__device__ __forceinline__ void finish_triangle(const DSceneView& sc, const HitRec& h, Surface& s) {
+    const DAttr* at = sc.attrs + h.slot;
+    const double w = 1.0 - h.u - h.v;
+    const double* n = &at->n[0][0];
+    const double2 a0 = ldg2(n), a1 = ldg2(n + 2), a2 = ldg2(n + 4), a3 = ldg2(n + 6);
+    const double a4 = __ldg(n + 8);
+    const D3 n0 = mk(a0.x, a0.y, a1.x), n1 = mk(a1.y, a2.x, a2.y), n2 = mk(a3.x, a3.y, a4);
+    s.normal = (w * n0 + h.u * n1) + h.v * n2;  // hittable.rs:105, not renormalised
+    const double* uv = &at->uv[0][0];
+    const double2 u0 = ldg2(uv), u1 = ldg2(uv + 2), u2 = ldg2(uv + 4);
+    s.u = (w * u0.x + h.u * u1.x) + h.v * u2.x;  // hittable.rs:106
+    s.v = (w * u0.y + h.u * u1.y) + h.v * u2.y;
+}
+
+__device__ __forceinline__ void finish_sphere(const DSceneView& sc, const HitRec& h, Surface& s) {
+    const DPrim* p = sc.prims + h.slot;
+    const double* pd = reinterpret_cast<const double*>(p);
+    const double2 q0 = ldg2(pd), q1 = ldg2(pd + 2);
+    const D3 center = mk(q0.x, q0.y, q1.x);
+    s.normal = normalize(s.position - center);  // hittable.rs:60
+    s.u = 0.5 - atan2(s.normal.z, s.normal.x) / kTau;  // hittable.rs:61
+    s.v = asin(s.normal.y) / kPi + 0.5;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels: ray batches
+// ---------------------------------------------------------------------------------------------
+
+template <bool COUNT, bool FULL>
+__global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+                                                            Counters* counters) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    LocalCounters lc = {0, 0, 0, 0};
+    if (i < n) {
+        const double2* rp = reinterpret_cast<const double2*>(rays + i);
+        const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+        const D3 o = mk(r0.x, r0.y, r1.x), d = mk(r1.y, r2.x, r2.y);
+        HitRec h;
+        h.t = r3.y; h.u = 0.0; h.v = 0.0; h.kind = 0;
+        closest_hit<COUNT>(sc, o, d, r3.x, h, lc);
+        if (FULL) {
+            rtp_hit_full* o_full = static_cast<rtp_hit_full*>(out) + i;
+            rtp_hit_full r;
+            if (h.slot != kNoPrim) {
+                Surface s;
+                finish_hit(sc, o, d, h, s);
+                if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
+                else finish_sphere(sc, h, s);
+                r.leaf = s.leaf; r.material = s.material; r.t = h.t;
+                r.position[0] = s.position.x; r.position[1] = s.position.y; r.position[2] = s.position.z;
+                r.normal[0] = s.normal.x; r.normal[1] = s.normal.y; r.normal[2] = s.normal.z;
+                r.uv[0] = s.u; r.uv[1] = s.v;
+            } else {
+                memset(&r, 0, sizeof r);
+                r.leaf = RTP_MISS; r.material = RTP_MISS; r.t = CUDART_INF;
+            }
+            *o_full = r;
+        } else {
+            uint4 w;
+            if (h.slot != kNoPrim) {
+                const DPrim* p = sc.prims + h.slot;
+                w.x = __ldg(&p->leaf); w.y = __ldg(&p->material);
+                const unsigned long long tb = static_cast<unsigned long long>(__double_as_longlong(h.t));
+                w.z = static_cast<uint32_t>(tb); w.w = static_cast<uint32_t>(tb >> 32);
+            } else {
+                w.x = RTP_MISS; w.y = RTP_MISS;
+                w.z = 0u; w.w = 0x7FF00000u;  // +inf
+            }
+            reinterpret_cast<uint4*>(out)[i] = w;
+        }
+    }
+    if (counters) {
+        // one atomic per warp per counter
+        unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests;
+        for (int off = 16; off; off >>= 1) {
+            r += __shfl_down_sync(0xffffffffu, r, off);
+            if (COUNT) {
+                nv += __shfl_down_sync(0xffffffffu, nv, off);
+                tt += __shfl_down_sync(0xffffffffu, tt, off);
+                st += __shfl_down_sync(0xffffffffu, st, off);
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&counters->rays, static_cast<unsigned long long>(r));
+            if (COUNT) {
+                atomicAdd(&counters->node_visits, static_cast<unsigned long long>(nv));
+                atomicAdd(&counters->triangle_tests, static_cast<unsigned long long>(tt));
+                atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera (render.rs:32-52) — tan(fov/2) is evaluated on the host (glibc, like the reference's
+// f64::tan) and passed in, so no device transcendental sits on the primary-ray path.
+// ---------------------------------------------------------------------------------------------
+
+struct DCamera {
+    double tan_fov, focal_dist, aspect_ratio, lens_radius;
+    double m[9];  // orientation, columns x, y, z
+    double pos[3];
+};
+
+__device__ __forceinline__ void camera_shoot(const DCamera& cam, double u, double v, double lens_x, double lens_y, D3& o, D3& d) {
+    const D3 origin = mk(lens_x, lens_y, 0.0);
+    const D3 target = mk((2.0 * u - 1.0) * cam.tan_fov * cam.focal_dist * cam.aspect_ratio, (2.0 * v - 1.0) * cam.tan_fov * cam.focal_dist,
+                         -cam.focal_dist);
+    const D3 dir = normalize(target - origin);
+    const double* m = cam.m;
+    // utility.rs:185-191: orientation * v accumulates column by column
+    d = mk((m[0] * dir.x + m[3] * dir.y) + m[6] * dir.z, (m[1] * dir.x + m[4] * dir.y) + m[7] * dir.z,
+           (m[2] * dir.x + m[5] * dir.y) + m[8] * dir.z);
+    o = mk(((m[0] * origin.x + m[3] * origin.y) + m[6] * origin.z) + cam.pos[0], ((m[1] * origin.x + m[4] * origin.y) + m[7] * origin.z) + cam.pos[1],
+           ((m[2] * origin.x + m[5] * origin.y) + m[8] * origin.z) + cam.pos[2]);
+}
+
+__global__ void __launch_bounds__(256) camera_rays_kernel(DCamera cam, uint32_t width, uint32_t height, rtp_ray* __restrict__ rays) {
+    const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t n = static_cast<size_t>(width) * height;
+    if (p >= n) return;
+    const uint32_t i = static_cast<uint32_t>(p % width), j = static_cast<uint32_t>(p / width);
+    const double u = (static_cast<double>(i) + 0.5) / static_cast<double>(width);
+    const double v = (static_cast<double>(j) + 0.5) / static_cast<double>(height);
+    D3 o, d;
+    camera_shoot(cam, u, v, 0.0, 0.0, o, d);
+    double2* out = reinterpret_cast<double2*>(rays + p);
+    out[0] = make_double2(o.x, o.y);
+    out[1] = make_double2(o.z, d.x);
+    out[2] = make_double2(d.y, d.z);
+    out[3] = make_double2(kRayEpsilon, CUDART_INF);
+}
+
+// ---------------------------------------------------------------------------------------------
+// random stream (replaces StdRng; layout in rtp.h)
+// ---------------------------------------------------------------------------------------------
+
+struct Rng {
+    uint32_t k0, k1, c0, c1, c3;
+    uint32_t k;       // next draw
+    uint32_t cached;  // block held in b0..b3
+    uint32_t b0, b1, b2, b3;
+};
+
+__device__ __forceinline__ void rng_init(Rng& r, unsigned long long seed, uint32_t lo, uint32_t hi, uint32_t stream) {
+    r.k0 = static_cast<uint32_t>(seed); r.k1 = static_cast<uint32_t>(seed >> 32);
+    r.c0 = lo; r.c1 = hi; r.c3 = stream;
+    r.k = 0; r.cached = 0xFFFFFFFFu;
+    r.b0 = r.b1 = r.b2 = r.b3 = 0;
+}
+
+__device__ __forceinline__ void philox_block(Rng& r, uint32_t block) {
+    uint32_t c0 = r.c0, c1 = r.c1, c2 = block, c3 = r.c3, k0 = r.k0, k1 = r.k1;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    r.b0 = c0; r.b1 = c1; r.b2 = c2; r.b3 = c3;
+    r.cached = block;
+}
+
+// rng.gen::<f64>() with rand 0.8's Standard mapping: 53 high bits * 2^-53
+__device__ __forceinline__ double rng_next(Rng& r) {
+    const uint32_t block = r.k >> 1, pair = r.k & 1u;
+    if (block != r.cached) philox_block(r, block);
+    r.k++;
+    const uint32_t lo = pair ? r.b2 : r.b0, hi = pair ? r.b3 : r.b1;
+    const unsigned long long u = (static_cast<unsigned long long>(hi) << 32) | lo;
+    return static_cast<double>(u >> 11) * 0x1.0p-53;
+}
+
+// randomness.rs:21-34 / 39-53 / 58-73
+__device__ __forceinline__ void sample_unit_disk(Rng& r, double& x, double& y) {
+    for (;;) {
+        const double vx = 2.0 * rng_next(r) - 1.0;
+        const double vy = 2.0 * rng_next(r) - 1.0;
+        if (0.0 + (vx * vx + vy * vy) < 1.0) { x = vx; y = vy; return; }
+    }
+}
+__device__ __forceinline__ D3 sample_unit_ball(Rng& r) {
+    for (;;) {
+        D3 v;
+        v.x = 2.0 * rng_next(r) - 1.0;
+        v.y = 2.0 * rng_next(r) - 1.0;
+        v.z = 2.0 * rng_next(r) - 1.0;
+        if (norm_squared(v) < 1.0) return v;
+    }
+}
+__device__ __forceinline__ D3 sample_unit_sphere(Rng& r) {
+    for (;;) {
+        const double vx = 2.0 * rng_next(r) - 1.0;
+        const double vy = 2.0 * rng_next(r) - 1.0;
+        const double s = 0.0 + (vx * vx + vy * vy);
+        if (s < 1.0) {
+            const double n = 2.0 * sqrt(1.0 - s);
+            return mk(vx * n, vy * n, 1.0 - 2.0 * s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// textures (texture.rs) and materials (material.rs)
+// ---------------------------------------------------------------------------------------------
+
+// Rust `as u32` / `as isize`: saturating, NaN -> 0
+__device__ __forceinline__ uint32_t sat_u32(double x) { return __double2uint_rz(x); }  // cvt.rzi.u32.f64 saturates, NaN -> 0
+__device__ __forceinline__ long long sat_i64(double x) { return __double2ll_rz(x); }   // cvt.rzi.s64.f64 saturates, NaN -> 0
+// f64::clamp: NaN stays NaN
+__device__ __forceinline__ double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// randomness.rs:91-110
+__device__ __forceinline__ long long noise_integer(long long x, long long y, long long z, long long seed) {
+    const unsigned long long A = 0x369E6D3B899E43CFull, B = 0x53F89E7FFDA3B07Dull, C = 0x3B13C1CA4937E629ull, D = 0x577C2C6E4019D645ull;
+    unsigned long long h = A * static_cast<unsigned long long>(x) + B * static_cast<unsigned long long>(y) + C * static_cast<unsigned long long>(z) +
+                           D * static_cast<unsigned long long>(seed);
+    h = static_cast<unsigned long long>(static_cast<long long>(h) >> 13) ^ h;
+    h = h * (h * h * 60493ull + 19990303ull) + 1376312589ull;
+    return static_cast<long long>(h);
+}
+__device__ __forceinline__ double noise_real(long long x, long long y, long long z, long long seed) {
+    return static_cast<double>(noise_integer(x, y, z, seed)) / 9223372036854775808.0;
+}
+__device__ __forceinline__ double grad_dot(D3 p, long long cx, long long cy, long long cz, long long seed) {  // texture.rs:70-76
+    const D3 g = mk(noise_real(cx, cy, cz, seed + 1), noise_real(cx, cy, cz, seed + 2), noise_real(cx, cy, cz, seed + 3));
+    return dot(p - mk(static_cast<double>(cx), static_cast<double>(cy), static_cast<double>(cz)), g);
+}
+__device__ __forceinline__ double mixd(double a, double b, double t) { return (b - a) * t + a; }
+__device__ __forceinline__ double smootherstep(double t) { return (t * (t * 6.0 - 15.0) + 10.0) * t * t * t; }
+
+// texture.rs:20-36 Texture::sample. Checker recursion (texture.rs:51-60) is unrolled into a bounded loop;
+// the reference would overflow its stack on a cyclic checker, here 64 hops yield black.
+__device__ D3 texture_sample(const DSceneView& sc, uint32_t tid, D3 position, double hu, double hv) {
+    for (int hop = 0; hop < 64; ++hop) {
+        const DTexture* tx = sc.textures + tid;
+        const uint32_t kind = __ldg(&tx->kind);
+        switch (kind) {
+            case RTP_TEXTURE_MISSING: return mk(0.0, 0.0, 0.0);
+            case RTP_TEXTURE_DEBUG_UVS: return mk(hu, hv, 0.0);
+            case RTP_TEXTURE_SOLID: return mk(__ldg(&tx->rgb[0]), __ldg(&tx->rgb[1]), __ldg(&tx->rgb[2]));
+            case RTP_TEXTURE_IMAGE: {  // texture.rs:40-49
+                const uint32_t wi = __ldg(&tx->width), hi = __ldg(&tx->height);
+                const double w = static_cast<double>(wi), h = static_cast<double>(hi);
+                const uint32_t i = sat_u32(clampd(hu * w, 0.0, w - 1.0));
+                const uint32_t j = sat_u32(clampd(hv * h, 0.0, h - 1.0));
+                const uchar4* texels = reinterpret_cast<const uchar4*>(tx->rgba);
+                const uchar4 px = __ldg(texels + (static_cast<size_t>(i) + static_cast<size_t>(j) * wi));  // image.rs:31-33
+                return mk(static_cast<double>(px.x) / 255.0, static_cast<double>(px.y) / 255.0, static_cast<double>(px.z) / 255.0);
+            }
+            case RTP_TEXTURE_CHECKER: {
+                const double sum = floor(position.x) + floor(position.y) + floor(position.z);
+                tid = (fmod(sum, 2.0) == 0.0) ? __ldg(&tx->even) : __ldg(&tx->odd);
+                continue;
+            }
+            case RTP_TEXTURE_NOISE: {  // texture.rs:62-68
+                double x = noise_real(sat_i64(floor(position.x)), sat_i64(floor(position.y)), sat_i64(floor(position.z)), tx->seed);
+                x = 0.5 * x + 0.5;
+                return mk(x, x, x);
+            }
+            case RTP_TEXTURE_PERLIN: {  // texture.rs:82-119
+                const D3 p = position;
+                const D3 fp = mk(floor(p.x), floor(p.y), floor(p.z));
+                const long long flx = sat_i64(fp.x), fly = sat_i64(fp.y), flz = sat_i64(fp.z);
+                const long long clx = flx + 1, cly = fly + 1, clz = flz + 1;
+                const long long seed = tx->seed;
+                const double k1 = grad_dot(p, flx, fly, flz, seed), k2 = grad_dot(p, clx, fly, flz, seed);
+                const double k3 = grad_dot(p, flx, cly, flz, seed), k4 = grad_dot(p, clx, cly, flz, seed);
+                const double k5 = grad_dot(p, flx, fly, clz, seed), k6 = grad_dot(p, clx, fly, clz, seed);
+                const double k7 = grad_dot(p, flx, cly, clz, seed), k8 = grad_dot(p, clx, cly, clz, seed);
+                D3 t = p - fp;
+                t = mk(smootherstep(t.x), smootherstep(t.y), smootherstep(t.z));
+                const double k12 = mixd(k1, k2, t.x), k34 = mixd(k3, k4, t.x), k56 = mixd(k5, k6, t.x), k78 = mixd(k7, k8, t.x);
+                const double k1234 = mixd(k12, k34, t.y), k5678 = mixd(k56, k78, t.y);
+                const double x = 0.5 * mixd(k1234, k5678, t.z) + 0.5;
+                return mk(x, x, x);
+            }
+            default: return mk(0.0, 0.0, 0.0);
+        }
+    }
+    return mk(0.0, 0.0, 0.0);
+}
+
+// material.rs:49-60 Emit::evaluate
+__device__ __forceinline__ D3 emit_evaluate(const DSceneView& sc, uint32_t kind, uint32_t tex, const double* rgb, D3 dir, D3 position, D3 normal,
+                                            double hu, double hv) {
+    switch (kind) {
+        case RTP_EMIT_COLOR: return mk(rgb[0], rgb[1], rgb[2]);
+        case RTP_EMIT_DEBUG_NORMALS: return normal;
+        case RTP_EMIT_SKY_GRADIENT: {
+            const double t = 0.5 * (dir.y / norm(dir) + 1.0);
+            const double a = 1.0 - t;
+            return mk(a * 1.0 + t * 0.5, a * 1.0 + t * 0.7, a * 1.0 + t * 1.0);
+        }
+        case RTP_EMIT_SKY_SPHERE: return texture_sample(sc, tex, position, hu, hv);
+        default: return mk(0.0, 0.0, 0.0);
+    }
+}
+
+// utility.rs:106-108
+__device__ __forceinline__ D3 reflect(D3 incident, D3 normal) { return incident - (2.0 * dot(incident, normal)) * normal; }
+
+// ---------------------------------------------------------------------------------------------
+// K2-K6: one thread per camera path (main.rs:70-83 + render.rs:94-146). Per-sample colours go to a
+// scratch buffer and are summed in sample order by resolve_kernel, which reproduces the
+// reference's sequential `final_color += …` (main.rs:80) bit for bit.
+// ---------------------------------------------------------------------------------------------
+
+struct DRender {
+    uint32_t width, height, max_bounce;
+    uint32_t tile_x, tile_y, tile_w, tile_h;
+    uint32_t sample_begin;  // first sample of this launch
+    uint32_t n_samples;     // samples per pixel in this launch
+    uint32_t _pad;
+    unsigned long long seed;
+};
+
+template <int MAXB, bool COUNT>
+__global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamera cam, DRender rp, double4* __restrict__ scratch,
+                                                            Counters* counters) {
+    const size_t npix = static_cast<size_t>(rp.tile_w) * rp.tile_h;
+    const size_t total = npix * rp.n_samples;
+    const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    LocalCounters lc = {0, 0, 0, 0};
+    if (p < total) {
+        const uint32_t s_local = static_cast<uint32_t>(p / npix);
+        const size_t pix = p % npix;
+        const uint32_t i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
+        const uint32_t j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+        const uint32_t smp = rp.sample_begin + s_local;
+
+        Rng rng;
+        rng_init(rng, rp.seed, j * rp.width + i, smp, RTP_RNG_STREAM_PATH);
+        // render.rs:76-81 make_uv_jitter
+        const double u = (static_cast<double>(i) + rng_next(rng)) / static_cast<double>(rp.width);
+        const double v = (static_cast<double>(j) + rng_next(rng)) / static_cast<double>(rp.height);
+        double lx, ly;
+        sample_unit_disk(rng, lx, ly);  // drawn even when lens_radius == 0 (render.rs:36)
+        D3 o, d;
+        camera_shoot(cam, u, v, cam.lens_radius * lx, cam.lens_radius * ly, o, d);
+
+        double emit_stack[MAXB][3], absorb_stack[MAXB][3];
+        int nb = 0;
+        D3 L = mk(0.0, 0.0, 0.0);
+        uint32_t depth = rp.max_bounce;
+        bool first = true, first_hit = false;
+        for (;;) {
+            if (!first && depth == 0) { L = mk(0.0, 0.0, 0.0); break; }  // render.rs:128-131
+            HitRec h;
+            h.t = CUDART_INF; h.u = 0.0; h.v = 0.0; h.kind = 0;
+            closest_hit<COUNT>(sc, o, d, kRayEpsilon, h, lc);
+            if (h.slot == kNoPrim) {
+                // render.rs:118,144 + utility.rs:93-100 Hit::at_infinity
+                const double hu = 0.5 - atan2(d.z, d.x) / kTau, hv = asin(d.y) / kPi + 0.5;
+                L = emit_evaluate(sc, sc.bg_kind, sc.bg_texture, sc.bg_rgb, d, d, d, hu, hv);
+                break;
+            }
+            if (first) first_hit = true;
+            Surface s;
+            finish_hit(sc, o, d, h, s);
+            if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
+            else finish_sphere(sc, h, s);
+            const DMaterial* m = sc.materials + s.material;
+
+            // material.rs:104-110: scatter, then absorb, then emit
+            bool scattered = false;
+            D3 sd = mk(0.0, 0.0, 0.0);
+            const uint32_t scatter = __ldg(&m->scatter);
+            if (scatter == RTP_SCATTER_LAMBERT) {  // material.rs:115-130
+                if (!(dot(s.normal, d) > 0.0)) {
+                    sd = normalize(s.normal + sample_unit_sphere(rng));
+                    scattered = true;
+                }
+            } else if (scatter == RTP_SCATTER_METAL) {  // material.rs:132-152
+                if (!(dot(s.normal, d) > 0.0)) {
+                    const D3 refl = reflect(d, s.normal);
+                    const D3 fz = __ldg(&m->scatter_param) * sample_unit_ball(rng);
+                    sd = normalize(refl + fz);
+                    scattered = !(dot(s.normal, sd) < 0.0);
+                }
+            } else if (scatter == RTP_SCATTER_DIELECTRIC) {  // material.rs:154-180
+                const double ior = __ldg(&m->scatter_param);
+                double eta;
+                D3 n;
+                if (dot(s.normal, d) > 0.0) { eta = ior; n = mk(-s.normal.x, -s.normal.y, -s.normal.z); }
+                else { eta = 1.0 / ior; n = s.normal; }
+                const double q = (1.0 - eta) / (1.0 + eta);
+                const double r0 = q * q;  // powi(2)
+                const double x = 1.0 + dot(n, d);
+                const double x2 = x * x;
+                const double reflectance = r0 + (1.0 - r0) * (x * (x2 * x2));  // powi(5)
+                if (rng_next(rng) < reflectance) {
+                    sd = reflect(d, n);
+                } else {  // utility.rs:110-119 refract, else reflect
+                    const double cos_theta = dot(n, d);
+                    const double k = 1.0 - eta * eta * (1.0 - cos_theta * cos_theta);
+                    if (k < 0.0) sd = reflect(d, n);
+                    else sd = eta * d - (eta * cos_theta + sqrt(k)) * n;
+                }
+                scattered = true;
+            }
+            D3 absorb;
+            switch (__ldg(&m->absorb)) {  // material.rs:74-81
+                case RTP_ABSORB_WHITEBODY: absorb = mk(1.0, 1.0, 1.0); break;
+                case RTP_ABSORB_ALBEDO: absorb = mk(__ldg(&m->absorb_rgb[0]), __ldg(&m->absorb_rgb[1]), __ldg(&m->absorb_rgb[2])); break;
+                case RTP_ABSORB_ALBEDO_MAP: absorb = texture_sample(sc, __ldg(&m->absorb_texture), s.position, s.u, s.v); break;
+                default: absorb = mk(0.0, 0.0, 0.0); break;
+            }
+            const D3 emit = emit_evaluate(sc, __ldg(&m->emit_kind), __ldg(&m->emit_texture), m->emit_rgb, d, s.position, s.normal, s.u, s.v);
+            if (!scattered) {  // render.rs:108-110: emit + rgb(0,0,0)
+                L = emit + mk(0.0, 0.0, 0.0);
+                break;
+            }
+            emit_stack[nb][0] = emit.x; emit_stack[nb][1] = emit.y; emit_stack[nb][2] = emit.z;
+            absorb_stack[nb][0] = absorb.x; absorb_stack[nb][1] = absorb.y; absorb_stack[nb][2] = absorb.z;
+            ++nb;
+            o = s.position; d = sd;
+            depth -= 1;
+            first = false;
+        }
+        // render.rs:108-115 / 135-142: emit + absorb ⊙ (inner), folded inside-out like the recursion
+        for (int b = nb - 1; b >= 0; --b) {
+            L = mk(emit_stack[b][0], emit_stack[b][1], emit_stack[b][2]) + cmul(mk(absorb_stack[b][0], absorb_stack[b][1], absorb_stack[b][2]), L);
+        }
+        scratch[p] = make_double4(L.x, L.y, L.z, first_hit ? 1.0 : 0.0);
+    }
+    if (counters) {
+        unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests;
+        for (int off = 16; off; off >>= 1) {
+            r += __shfl_down_sync(0xffffffffu, r, off);
+            if (COUNT) {
+                nv += __shfl_down_sync(0xffffffffu, nv, off);
+                tt += __shfl_down_sync(0xffffffffu, tt, off);
+                st += __shfl_down_sync(0xffffffffu, st, off);
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&counters->rays, static_cast<unsigned long long>(r));
+            if (COUNT) {
+                atomicAdd(&counters->node_visits, static_cast<unsigned long long>(nv));
+                atomicAdd(&counters->triangle_tests, static_cast<unsigned long long>(tt));
+                atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
+            }
+        }
+    }
+}
+
+// main.rs:78-87: per pixel, add the samples of this launch in sample order to the running sums; on the
+// last launch optionally divide by num_samples. acc is (r,g,b,foreground) per tile pixel.
+__global__ void __launch_bounds__(256) resolve_kernel(const double4* __restrict__ scratch, double4* __restrict__ acc, size_t npix, uint32_t n_samples,
+                                                       int first_launch) {
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    double4 a = first_launch ? make_double4(0.0, 0.0, 0.0, 0.0) : acc[pix];
+    for (uint32_t s = 0; s < n_samples; ++s) {
+        const double4 c = scratch[static_cast<size_t>(s) * npix + pix];
+        a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+    }
+    acc[pix] = a;
+}
+
+__global__ void __launch_bounds__(256) write_frame_kernel(const double4* __restrict__ acc, DRender rp, double divisor, double* __restrict__ rgb,
+                                                           double* __restrict__ fg) {
+    const size_t npix = static_cast<size_t>(rp.tile_w) * rp.tile_h;
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const uint32_t i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
+    const uint32_t j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+    const size_t px = static_cast<size_t>(i) + static_cast<size_t>(j) * rp.width;
+    double4 a = acc[pix];
+    if (divisor != 0.0) { a.x = a.x / divisor; a.y = a.y / divisor; a.z = a.z / divisor; a.w = a.w / divisor; }
+    rgb[3 * px + 0] = a.x; rgb[3 * px + 1] = a.y; rgb[3 * px + 2] = a.z;
+    if (fg) fg[px] = a.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device scene
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kPipeDepth = 3;
+constexpr size_t kChunkRays = 1u << 18;  // 16 MiB of rays per pipeline stage
+
+struct DeviceScene {
+    int device = 0;
+    DNode* nodes = nullptr;
+    DPrim* prims = nullptr;
+    DAttr* attrs = nullptr;
+    DMaterial* materials = nullptr;
+    DTexture* textures = nullptr;
+    std::vector<uint8_t*> images;
+    DSceneView view{};
+    uint64_t bytes = 0;
+
+    std::mutex lock;  // serialises calls that use the scratch below
+    Counters* counters = nullptr;
+    cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
+    void* stage_hits[kPipeDepth] = {nullptr, nullptr, nullptr};
+    double4* scratch = nullptr; size_t scratch_elems = 0;
+    double4* acc = nullptr; size_t acc_elems = 0;
+    double* frame = nullptr; size_t frame_elems = 0;
+};
+
+template <class T>
+static int upload(const std::vector<T>& v, T** out, uint64_t* bytes) {
+    const size_t n = std::max<size_t>(v.size(), 1);
+    RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(out), n * sizeof(T)));
+    if (!v.empty()) RTP_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *bytes += n * sizeof(T);
+    return RTP_OK;
+}
+
+void device_scene_free(DeviceScene* ds) {
+    if (!ds) return;
+    cudaFree(ds->nodes); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
+    for (uint8_t* p : ds->images) cudaFree(p);
+    cudaFree(ds->counters);
+    for (int k = 0; k < kPipeDepth; ++k) {
+        if (ds->streams[k]) cudaStreamDestroy(ds->streams[k]);
+        cudaFree(ds->stage_rays[k]); cudaFree(ds->stage_hits[k]);
+    }
+    if (ds->ev_begin) cudaEventDestroy(ds->ev_begin);
+    if (ds->ev_end) cudaEventDestroy(ds->ev_end);
+    cudaFree(ds->scratch); cudaFree(ds->acc); cudaFree(ds->frame);
+    delete ds;
+}
+
+uint64_t device_scene_bytes(const DeviceScene* ds) { return ds ? ds->bytes : 0; }
+
+static int g_device = -1;
+
+static int require_device() {
+    if (g_device >= 0) return RTP_OK;
+    return rtp_init(0);
+}
+
+int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
+    int rc = require_device();
+    if (rc != RTP_OK) return rc;
+    DeviceScene* ds = new DeviceScene();
+    ds->device = g_device;
+    auto bail = [&](int code) { device_scene_free(ds); return code; };
+    if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
+    if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
+    if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
+    if ((rc = upload(flat.materials, &ds->materials, &ds->bytes)) != RTP_OK) return bail(rc);
+    std::vector<DTexture> tex = flat.textures;
+    ds->images.assign(tex.size(), nullptr);
+    for (size_t i = 0; i < tex.size(); ++i) {
+        if (flat.images[i].empty()) continue;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ds->images[i]), flat.images[i].size());
+        if (e == cudaSuccess) e = cudaMemcpy(ds->images[i], flat.images[i].data(), flat.images[i].size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(set_error(RTP_ERR_CUDA, std::string("texture upload: ") + cudaGetErrorString(e)));
+        tex[i].rgba = ds->images[i];
+        ds->bytes += flat.images[i].size();
+    }
+    if ((rc = upload(tex, &ds->textures, &ds->bytes)) != RTP_OK) return bail(rc);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ds->counters), sizeof(Counters));
+    for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_end);
+    if (e != cudaSuccess) return bail(set_error(RTP_ERR_CUDA, std::string("scene resources: ") + cudaGetErrorString(e)));
+
+    DSceneView& v = ds->view;
+    v.nodes = ds->nodes; v.prims = ds->prims; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
+    v.n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
+    v.n_prims = static_cast<uint32_t>(flat.prims.size());
+    v.root_kind = flat.root_kind;
+    v.bg_kind = flat.background.kind; v.bg_texture = flat.background.texture;
+    std::memcpy(v.bg_rgb, flat.background.rgb, sizeof v.bg_rgb);
+    *out = ds;
+    return RTP_OK;
+}
+
+static DCamera make_camera(const rtp_camera* c) {
+    DCamera d;
+    d.tan_fov = std::tan(0.5 * c->fov);  // render.rs:33, evaluated by the host libm like the reference
+    d.focal_dist = c->focal_dist; d.aspect_ratio = c->aspect_ratio; d.lens_radius = c->lens_radius;
+    std::memcpy(d.m, c->orientation, sizeof d.m);
+    std::memcpy(d.pos, c->position, sizeof d.pos);
+    return d;
+}
+
+static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* d_out, bool full, bool count, Counters* counters,
+                        cudaStream_t stream) {
+    if (n == 0) return RTP_OK;
+    const unsigned block = 128;
+    const size_t grid = (n + block - 1) / block;
+    if (grid > 0x7FFFFFFFull) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
+    const dim3 g(static_cast<unsigned>(grid));
+    if (full) {
+        if (count) trace_closest_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+        else trace_closest_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+    } else {
+        if (count) trace_closest_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+        else trace_closest_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+    }
+    RTP_CUDA(cudaGetLastError());
+    return RTP_OK;
+}
+
+// Host-buffer batch: chunks flow H2D → kernel → D2H on kPipeDepth streams so copies overlap traversal.
+static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hits_out, bool full, rtp_stats* stats) {
+    DeviceScene* ds = scene->dev;
+    std::lock_guard<std::mutex> guard(ds->lock);
+    RTP_CUDA(cudaSetDevice(ds->device));
+    const size_t hit_bytes = full ? sizeof(rtp_hit_full) : sizeof(rtp_hit);
+    for (int k = 0; k < kPipeDepth; ++k) {
+        if (!ds->stage_rays[k]) RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->stage_rays[k]), kChunkRays * sizeof(rtp_ray)));
+        if (!ds->stage_hits[k]) RTP_CUDA(cudaMalloc(&ds->stage_hits[k], kChunkRays * sizeof(rtp_hit_full)));
+    }
+    const bool count = stats != nullptr;
+    if (count) RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), ds->streams[0]));
+    RTP_CUDA(cudaEventRecord(ds->ev_begin, ds->streams[0]));
+    for (int k = 1; k < kPipeDepth; ++k) RTP_CUDA(cudaStreamWaitEvent(ds->streams[k], ds->ev_begin, 0));
+    size_t launches = 0, chunk_id = 0;
+    for (size_t off = 0; off < n; off += kChunkRays, ++chunk_id) {
+        const size_t m = std::min(kChunkRays, n - off);
+        const int k = static_cast<int>(chunk_id % kPipeDepth);
+        cudaStream_t st = ds->streams[k];
+        RTP_CUDA(cudaMemcpyAsync(ds->stage_rays[k], rays + off, m * sizeof(rtp_ray), cudaMemcpyHostToDevice, st));
+        int rc = launch_trace(ds, ds->stage_rays[k], m, ds->stage_hits[k], full, false, count ? ds->counters : nullptr, st);
+        if (rc != RTP_OK) return rc;
+        ++launches;
+        RTP_CUDA(cudaMemcpyAsync(static_cast<char*>(hits_out) + off * hit_bytes, ds->stage_hits[k], m * hit_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    cudaEvent_t done[kPipeDepth];
+    for (int k = 1; k < kPipeDepth; ++k) {
+        RTP_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        RTP_CUDA(cudaEventRecord(done[k], ds->streams[k]));
+        RTP_CUDA(cudaStreamWaitEvent(ds->streams[0], done[k], 0));
+    }
+    RTP_CUDA(cudaEventRecord(ds->ev_end, ds->streams[0]));
+    RTP_CUDA(cudaEventSynchronize(ds->ev_end));
+    for (int k = 1; k < kPipeDepth; ++k) cudaEventDestroy(done[k]);
+    if (stats) {
+        Counters c;
+        RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
+        float ms = 0.f;
+        RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
+        std::memset(stats, 0, sizeof *stats);
+        stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests;
+        stats->device_ms = ms; stats->kernel_launches = launches;
+    }
+    return RTP_OK;
+}
+
+template <int MAXB>
+static void launch_render_paths(DeviceScene* ds, const DCamera& cam, const DRender& rp, size_t total, bool count, cudaStream_t st) {
+    const unsigned block = 128;
+    const dim3 g(static_cast<unsigned>((total + block - 1) / block));
+    if (count) render_paths_kernel<MAXB, true><<<g, block, 0, st>>>(ds->view, cam, rp, ds->scratch, ds->counters);
+    else render_paths_kernel<MAXB, false><<<g, block, 0, st>>>(ds->view, cam, rp, ds->scratch, ds->counters);
+}
+
+static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* p, double* d_rgb, double* d_fg, rtp_stats* stats,
+                         cudaStream_t st) {
+    DeviceScene* ds = scene->dev;
+    if (p->max_bounce < 1) return set_error(RTP_ERR_INVALID, "assert!(depth >= 1) (render.rs:97)");
+    if (p->max_bounce > 128) return set_error(RTP_ERR_UNSUPPORTED, "max_bounce > 128");
+    if (p->width == 0 || p->height == 0 || p->sample_end < p->sample_begin || p->num_samples == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
+    if (static_cast<uint64_t>(p->width) * p->height > 0xFFFFFFFFull) return set_error(RTP_ERR_INVALID, "frame too large");
+    const uint32_t tx = p->tile_x, ty = p->tile_y;
+    if (tx >= p->width || ty >= p->height) return set_error(RTP_ERR_INVALID, "tile outside frame");
+    const uint32_t tw = p->tile_w ? p->tile_w : p->width - tx, th = p->tile_h ? p->tile_h : p->height - ty;
+    if (static_cast<uint64_t>(tx) + tw > p->width || static_cast<uint64_t>(ty) + th > p->height) return set_error(RTP_ERR_INVALID, "tile outside frame");
+
+    const size_t npix = static_cast<size_t>(tw) * th;
+    const uint32_t ns_total = p->sample_end - p->sample_begin;
+    // samples per launch: bound the scratch buffer to ~256 MiB (8 Mi paths)
+    uint32_t per_launch = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(ns_total ? ns_total : 1, (size_t(8) << 20) / npix)));
+    const size_t need = npix * per_launch;
+    if (ds->scratch_elems < need) {
+        cudaFree(ds->scratch); ds->scratch = nullptr; ds->scratch_elems = 0;
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->scratch), need * sizeof(double4)));
+        ds->scratch_elems = need;
+    }
+    if (ds->acc_elems < npix) {
+        cudaFree(ds->acc); ds->acc = nullptr; ds->acc_elems = 0;
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->acc), npix * sizeof(double4)));
+        ds->acc_elems = npix;
+    }
+    const bool count = (p->flags & RTP_RENDER_COUNTERS) != 0;
+    const DCamera cam = make_camera(camera);
+    DRender rp;
+    rp.width = p->width; rp.height = p->height; rp.max_bounce = p->max_bounce;
+    rp.tile_x = tx; rp.tile_y = ty; rp.tile_w = tw; rp.tile_h = th;
+    rp._pad = 0; rp.seed = p->seed;
+
+    RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), st));
+    if (stats) RTP_CUDA(cudaEventRecord(ds->ev_begin, st));
+    size_t launches = 0;
+    bool first = true;
+    if (ns_total == 0) RTP_CUDA(cudaMemsetAsync(ds->acc, 0, npix * sizeof(double4), st));
+    for (uint32_t s0 = 0; s0 < ns_total; s0 += per_launch) {
+        rp.sample_begin = p->sample_begin + s0;
+        rp.n_samples = std::min(per_launch, ns_total - s0);
+        const size_t total = npix * rp.n_samples;
+        if (p->max_bounce <= 8) launch_render_paths<8>(ds, cam, rp, total, count, st);
+        else if (p->max_bounce <= 32) launch_render_paths<32>(ds, cam, rp, total, count, st);
+        else launch_render_paths<128>(ds, cam, rp, total, count, st);
+        RTP_CUDA(cudaGetLastError());
+        resolve_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, st>>>(ds->scratch, ds->acc, npix, rp.n_samples, first ? 1 : 0);
+        RTP_CUDA(cudaGetLastError());
+        launches += 2;
+        first = false;
+    }
+    const double divisor = (p->flags & RTP_RENDER_RAW_SUMS) ? 0.0 : static_cast<double>(p->num_samples);
+    write_frame_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, st>>>(ds->acc, rp, divisor, d_rgb, d_fg);
+    RTP_CUDA(cudaGetLastError());
+    ++launches;
+    if (stats) {
+        RTP_CUDA(cudaEventRecord(ds->ev_end, st));
+        RTP_CUDA(cudaEventSynchronize(ds->ev_end));
+        Counters c;
+        RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
+        float ms = 0.f;
+        RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
+        std::memset(stats, 0, sizeof *stats);
+        stats->rays = c.rays; stats->paths = static_cast<uint64_t>(npix) * ns_total;
+        stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests;
+        stats->device_ms = ms; stats->kernel_launches = launches;
+    }
+    return RTP_OK;
+}
+
+}  // namespace rtp
+
+// =============================================================================================
+// C ABI — device entry points
+// =============================================================================================
+
+using namespace rtp;
+
+extern "C" {
+
+int rtp_device_count(int* count) {
+    if (!count) return set_error(RTP_ERR_INVALID, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return set_error(RTP_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = n;
+    return RTP_OK;
+}
+
+int rtp_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(RTP_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                           " (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return set_error(RTP_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    RTP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return set_error(RTP_ERR_CUDA, std::string("device ") + prop.name + " is not compute capability 10.x; kernels are built for sm_100a only");
+    RTP_CUDA(cudaSetDevice(device));
+    RTP_CUDA(cudaFree(nullptr));
+    g_device = device;
+    return RTP_OK;
+}
+
+int rtp_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_error(RTP_ERR_INVALID, "null argument");
+    int rc = require_device();
+    if (rc != RTP_OK) return rc;
+    RTP_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return RTP_OK;
+}
+
+void rtp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
+    if (!out) return set_error(RTP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    try {
+        rtp_scene* s = new rtp_scene();
+        int rc = flatten_scene(desc, &s->flat);
+        if (rc == RTP_OK) rc = device_scene_upload(s->flat, &s->dev);
+        if (rc != RTP_OK) { delete s; return rc; }
+        s->n_leaves = static_cast<uint32_t>(s->flat.prims.size());
+        s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(s->flat.nodes.size()) : 0u;
+        // the host copies of the big arrays are no longer needed
+        std::vector<DNode>().swap(s->flat.nodes);
+        std::vector<DPrim>().swap(s->flat.prims);
+        std::vector<DAttr>().swap(s->flat.attrs);
+        std::vector<std::vector<uint8_t>>().swap(s->flat.images);
+        *out = s;
+        return RTP_OK;
+    } catch (const std::exception& e) {
+        return set_error(RTP_ERR_NOMEM, e.what());
+    }
+}
+
+void rtp_scene_destroy(rtp_scene* scene) {
+    if (!scene) return;
+    device_scene_free(scene->dev);
+    delete scene;
+}
+
+int rtp_scene_get_info(const rtp_scene* scene, rtp_scene_info* info) {
+    if (!scene || !info) return set_error(RTP_ERR_INVALID, "null argument");
+    info->n_leaves = scene->n_leaves; info->n_nodes = scene->n_nodes;
+    info->depth = scene->flat.depth; info->root_kind = scene->flat.root_kind;
+    info->device_bytes = device_scene_bytes(scene->dev);
+    return RTP_OK;
+}
+
+int rtp_bvh_build_order(const rtp_scene_desc* desc, uint32_t* leaf_ids_out, size_t cap, rtp_scene_info* info) {
+    try {
+        FlatScene flat;
+        int rc = flatten_scene(desc, &flat);
+        if (rc != RTP_OK) return rc;
+        if (leaf_ids_out) {
+            if (cap < flat.leaf_order.size()) return set_error(RTP_ERR_INVALID, "leaf_ids_out too small");
+            std::copy(flat.leaf_order.begin(), flat.leaf_order.end(), leaf_ids_out);
+        }
+        if (info) {
+            info->n_leaves = static_cast<uint32_t>(flat.prims.size());
+            info->n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
+            info->depth = flat.depth; info->root_kind = flat.root_kind; info->device_bytes = 0;
+        }
+        return RTP_OK;
+    } catch (const std::exception& e) {
+        return set_error(RTP_ERR_NOMEM, e.what());
+    }
+}
+
+int rtp_scene_leaf_order(const rtp_scene* scene, uint32_t* out, size_t cap) {
+    if (!scene || !out || cap < scene->flat.leaf_order.size()) return set_error(RTP_ERR_INVALID, "bad argument");
+    std::copy(scene->flat.leaf_order.begin(), scene->flat.leaf_order.end(), out);
+    return RTP_OK;
+}
+
+int rtp_trace_closest(rtp_scene* scene, const rtp_ray* rays, size_t n, rtp_hit* hits_out, rtp_stats* stats) {
+    if (!scene || (n && (!rays || !hits_out))) return set_error(RTP_ERR_INVALID, "null argument");
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (n == 0) return RTP_OK;
+    return trace_host(scene, rays, n, hits_out, false, stats);
+}
+
+int rtp_trace_closest_full(rtp_scene* scene, const rtp_ray* rays, size_t n, rtp_hit_full* hits_out, rtp_stats* stats) {
+    if (!scene || (n && (!rays || !hits_out))) return set_error(RTP_ERR_INVALID, "null argument");
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (n == 0) return RTP_OK;
+    return trace_host(scene, rays, n, hits_out, true, stats);
+}
+
+int rtp_trace_closest_device(rtp_scene* scene, const rtp_ray* d_rays, size_t n, rtp_hit* d_hits_out, void* cuda_stream) {
+    if (!scene || (n && (!d_rays || !d_hits_out))) return set_error(RTP_ERR_INVALID, "null argument");
+    RTP_CUDA(cudaSetDevice(scene->dev->device));
+    return launch_trace(scene->dev, d_rays, n, d_hits_out, false, false, nullptr, static_cast<cudaStream_t>(cuda_stream));
+}
+
+/* Counting variant used by tests and the roofline report: node visits / primitive tests for a device-resident batch. */
+int rtp_trace_closest_device_counted(rtp_scene* scene, const rtp_ray* d_rays, size_t n, rtp_hit* d_hits_out, rtp_stats* stats) {
+    if (!scene || !stats || (n && (!d_rays || !d_hits_out))) return set_error(RTP_ERR_INVALID, "null argument");
+    DeviceScene* ds = scene->dev;
+    std::lock_guard<std::mutex> guard(ds->lock);
+    RTP_CUDA(cudaSetDevice(ds->device));
+    cudaStream_t st = ds->streams[0];
+    RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), st));
+    RTP_CUDA(cudaEventRecord(ds->ev_begin, st));
+    int rc = launch_trace(ds, d_rays, n, d_hits_out, false, true, ds->counters, st);
+    if (rc != RTP_OK) return rc;
+    RTP_CUDA(cudaEventRecord(ds->ev_end, st));
+    RTP_CUDA(cudaEventSynchronize(ds->ev_end));
+    Counters c;
+    RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
+    std::memset(stats, 0, sizeof *stats);
+    stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests;
+    stats->device_ms = ms; stats->kernel_launches = 1;
+    return RTP_OK;
+}
+
+int rtp_camera_rays_device(const rtp_camera* camera, uint32_t width, uint32_t height, rtp_ray* d_rays_out, void* cuda_stream) {
+    if (!camera || !d_rays_out) return set_error(RTP_ERR_INVALID, "null argument");
+    int rc = require_device();
+    if (rc != RTP_OK) return rc;
+    const size_t n = static_cast<size_t>(width) * height;
+    if (n == 0) return RTP_OK;
+    const DCamera cam = make_camera(camera);
+    camera_rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(cam, width, height, d_rays_out);
+    RTP_CUDA(cudaGetLastError());
+    return RTP_OK;
+}
+
+int rtp_camera_rays(const rtp_camera* camera, uint32_t width, uint32_t height, rtp_ray* rays_out) {
+    if (!camera || !rays_out) return set_error(RTP_ERR_INVALID, "null argument");
+    int rc = require_device();
+    if (rc != RTP_OK) return rc;
+    const size_t n = static_cast<size_t>(width) * height;
+    if (n == 0) return RTP_OK;
+    rtp_ray* d = nullptr;
+    RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), n * sizeof(rtp_ray)));
+    rc = rtp_camera_rays_device(camera, width, height, d, nullptr);
+    cudaError_t e = rc == RTP_OK ? cudaMemcpy(rays_out, d, n * sizeof(rtp_ray), cudaMemcpyDeviceToHost) : cudaSuccess;
+    cudaFree(d);
+    if (rc != RTP_OK) return rc;
+    if (e != cudaSuccess) return set_error(RTP_ERR_CUDA, std::string("camera rays copy: ") + cudaGetErrorString(e));
+    return RTP_OK;
+}
+
+int rtp_render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, double* d_rgb_out, double* d_foreground_out,
+                      rtp_stats* stats, void* cuda_stream) {
+    if (!scene || !camera || !params || !d_rgb_out) return set_error(RTP_ERR_INVALID, "null argument");
+    DeviceScene* ds = scene->dev;
+    std::lock_guard<std::mutex> guard(ds->lock);
+    RTP_CUDA(cudaSetDevice(ds->device));
+    return render_device(scene, camera, params, d_rgb_out, d_foreground_out, stats, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int rtp_render(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, double* rgb_out, double* foreground_out,
+               rtp_stats* stats) {
+    if (!scene || !camera || !params || !rgb_out) return set_error(RTP_ERR_INVALID, "null argument");
+    DeviceScene* ds = scene->dev;
+    std::lock_guard<std::mutex> guard(ds->lock);
+    RTP_CUDA(cudaSetDevice(ds->device));
+    const size_t npx = static_cast<size_t>(params->width) * params->height;
+    if (npx == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
+    if (ds->frame_elems < npx * 4) {
+        cudaFree(ds->frame); ds->frame = nullptr; ds->frame_elems = 0;
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->frame), npx * 4 * sizeof(double)));
+        ds->frame_elems = npx * 4;
+    }
+    cudaStream_t st = ds->streams[0];
+    int rc = render_device(scene, camera, params, ds->frame, foreground_out ? ds->frame + npx * 3 : nullptr, stats, st);
+    if (rc != RTP_OK) return rc;
+    // only the tile rectangle was written (main.rs:86-87 writes per tile): copy back exactly those rows
+    const uint32_t W = params->width, tx = params->tile_x, ty = params->tile_y;
+    const uint32_t tw = params->tile_w ? params->tile_w : W - tx, th = params->tile_h ? params->tile_h : params->height - ty;
+    const size_t first = static_cast<size_t>(tx) + static_cast<size_t>(ty) * W;
+    RTP_CUDA(cudaMemcpy2DAsync(rgb_out + 3 * first, static_cast<size_t>(W) * 24, ds->frame + 3 * first, static_cast<size_t>(W) * 24,
+                               static_cast<size_t>(tw) * 24, th, cudaMemcpyDeviceToHost, st));
+    if (foreground_out)
+        RTP_CUDA(cudaMemcpy2DAsync(foreground_out + first, static_cast<size_t>(W) * 8, ds->frame + npx * 3 + first, static_cast<size_t>(W) * 8,
+                                   static_cast<size_t>(tw) * 8, th, cudaMemcpyDeviceToHost, st));
+    RTP_CUDA(cudaStreamSynchronize(st));
+    return RTP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,588 @@
+// rtp_host.cpp — host layer behind the C ABI: error plumbing, asset readers, the reference's
+// BVH construction and the flattening of a scene description into the device layout.
+//
+// Everything here runs once per scene (or per file); none of it is on the per-ray path.
+// Reference citations are file:line under /root/reference/src.
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <future>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "rtp_internal.h"
+
+namespace rtp {
+
+static thread_local std::string g_last_error;
+
+int set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// f64::min / f64::max (IEEE minNum / maxNum), as used by AABB::union and the triangle box.
+static inline double min_num(double a, double b) { return std::fmin(a, b); }
+static inline double max_num(double a, double b) { return std::fmax(a, b); }
+
+// nalgebra 0.29 reductions on static 3-vectors: (x*x' + y*y') + z*z'
+static inline double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+// --------------------------------------------------------------------------- BVH build --------
+
+struct BuildItem {
+    uint32_t id;  // LeafId
+    double bmin[3], bmax[3];
+};
+
+struct Builder {
+    std::vector<BuildItem>& items;
+    std::vector<DNode>& nodes;
+    std::atomic<uint32_t> depth{0};
+
+    // bvh.rs:36-56 make_bvh + bvh.rs:58-67 split, writing nodes straight into pre-order position.
+    // A range of n leaves occupies 2n-1 consecutive nodes starting at `base`; the left half
+    // [lo, lo+n/2) comes first. The reference sorts with sort_unstable_by, whose order among equal
+    // centroid keys is unspecified (it depends on the Rust std version); ties are broken by
+    // LeafId here, which makes the key a total order and the tree unique.
+    void build(size_t lo, size_t n, uint32_t base, int axis, uint32_t level, int spawn_levels) {
+        uint32_t seen = depth.load(std::memory_order_relaxed);
+        while (level > seen && !depth.compare_exchange_weak(seen, level, std::memory_order_relaxed)) {}
+        DNode& nd = nodes[base];
+        nd.skip = base + static_cast<uint32_t>(2 * n - 1);
+        nd._pad = 0;
+        if (n == 1) {
+            const BuildItem& it = items[lo];
+            std::memcpy(nd.bmin, it.bmin, sizeof nd.bmin);
+            std::memcpy(nd.bmax, it.bmax, sizeof nd.bmax);
+            nd.prim = static_cast<uint32_t>(lo);
+            nd.kind = 0;  // filled by the caller once primitives are laid out
+            return;
+        }
+        std::sort(items.begin() + lo, items.begin() + lo + n, [axis](const BuildItem& x, const BuildItem& y) {
+            double kx = 0.5 * (x.bmin[axis] + x.bmax[axis]);
+            double ky = 0.5 * (y.bmin[axis] + y.bmax[axis]);
+            if (kx != ky) return kx < ky;
+            return x.id < y.id;
+        });
+        size_t nl = n / 2, nr = n - nl;
+        uint32_t left = base + 1, right = base + 1 + static_cast<uint32_t>(2 * nl - 1);
+        int next_axis = (axis + 1) % 3;
+        if (spawn_levels > 0 && n > 65536) {
+            auto fut = std::async(std::launch::async, [=] { build(lo, nl, left, next_axis, level + 1, spawn_levels - 1); });
+            build(lo + nl, nr, right, next_axis, level + 1, spawn_levels - 1);
+            fut.get();
+        } else {
+            build(lo, nl, left, next_axis, level + 1, 0);
+            build(lo + nl, nr, right, next_axis, level + 1, 0);
+        }
+        const DNode& l = nodes[left];
+        const DNode& r = nodes[right];
+        for (int k = 0; k < 3; ++k) {  // utility.rs:130-135 AABB::union
+            nd.bmin[k] = min_num(l.bmin[k], r.bmin[k]);
+            nd.bmax[k] = max_num(l.bmax[k], r.bmax[k]);
+        }
+        nd.prim = kNoPrim;
+        nd.kind = 0;
+    }
+};
+
+static bool emit_ok(const rtp_emit& e, uint32_t n_textures) {
+    if (e.kind > RTP_EMIT_SKY_SPHERE) return false;
+    return e.kind != RTP_EMIT_SKY_SPHERE || e.texture < n_textures;
+}
+
+int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
+    if (!d || !out) return set_error(RTP_ERR_INVALID, "null scene description");
+    if (d->abi_version != RTP_ABI_VERSION) return set_error(RTP_ERR_INVALID, "rtp_scene_desc.abi_version mismatch");
+    if (d->root_kind > RTP_ROOT_LIST) return set_error(RTP_ERR_INVALID, "unknown root kind");
+    if ((d->n_meshes && !d->meshes) || (d->n_hittables && !d->hittables) || (d->n_materials && !d->materials) ||
+        (d->n_textures && !d->textures))
+        return set_error(RTP_ERR_INVALID, "null table with non-zero count");
+    if (d->root_kind == RTP_ROOT_BVH && d->n_hittables == 0)
+        return set_error(RTP_ERR_INVALID, "Bvh::new on an empty list is unreachable!() in the reference (bvh.rs:40)");
+    if (d->n_hittables >= 0x7FFFFFFFu) return set_error(RTP_ERR_INVALID, "too many hittables");
+
+    // ---- tables -------------------------------------------------------------------------
+    out->root_kind = d->root_kind;
+    out->background = d->background;
+    if (!emit_ok(d->background, d->n_textures)) return set_error(RTP_ERR_INVALID, "background emit is invalid");
+    out->textures.resize(d->n_textures);
+    out->images.resize(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const rtp_texture& t = d->textures[i];
+        if (t.kind > RTP_TEXTURE_PERLIN) return set_error(RTP_ERR_INVALID, "unknown texture kind");
+        DTexture& o = out->textures[i];
+        std::memset(&o, 0, sizeof o);
+        o.kind = t.kind; o.width = t.width; o.height = t.height; o.odd = t.odd; o.even = t.even; o.seed = t.seed;
+        std::memcpy(o.rgb, t.rgb, sizeof o.rgb);
+        if (t.kind == RTP_TEXTURE_IMAGE) {
+            size_t bytes = static_cast<size_t>(t.width) * t.height * 4;
+            if (!t.rgba || bytes == 0) return set_error(RTP_ERR_INVALID, "image texture without texels");
+            out->images[i].assign(t.rgba, t.rgba + bytes);
+        }
+        if (t.kind == RTP_TEXTURE_CHECKER && (t.odd >= d->n_textures || t.even >= d->n_textures))
+            return set_error(RTP_ERR_INVALID, "checker texture id out of range");
+    }
+    out->materials.resize(d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const rtp_material& m = d->materials[i];
+        if (m.scatter > RTP_SCATTER_DIELECTRIC || m.absorb > RTP_ABSORB_ALBEDO_MAP || !emit_ok(m.emit, d->n_textures) ||
+            (m.absorb == RTP_ABSORB_ALBEDO_MAP && m.absorb_texture >= d->n_textures))
+            return set_error(RTP_ERR_INVALID, "material " + std::to_string(i) + " is invalid");
+        DMaterial& o = out->materials[i];
+        std::memset(&o, 0, sizeof o);
+        o.scatter = m.scatter; o.absorb = m.absorb; o.absorb_texture = m.absorb_texture;
+        o.emit_kind = m.emit.kind; o.emit_texture = m.emit.texture;
+        o.scatter_param = m.scatter_param;
+        std::memcpy(o.absorb_rgb, m.absorb_rgb, sizeof o.absorb_rgb);
+        std::memcpy(o.emit_rgb, m.emit.rgb, sizeof o.emit_rgb);
+    }
+    for (uint32_t i = 0; i < d->n_meshes; ++i) {
+        const rtp_mesh& m = d->meshes[i];
+        if ((m.n_vertices && !m.vertices) || (m.n_indices && !m.indices)) return set_error(RTP_ERR_INVALID, "null mesh arrays");
+        if (m.material >= d->n_materials) return set_error(RTP_ERR_INVALID, "mesh material out of range");
+        for (uint32_t k = 0; k < m.n_indices; ++k)
+            if (m.indices[k] >= m.n_vertices) return set_error(RTP_ERR_INVALID, "vertex index out of range");
+    }
+
+    // ---- leaf boxes: hittable.rs:124-140 ---------------------------------------------------
+    const uint32_t n = d->n_hittables;
+    std::vector<BuildItem> items(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const rtp_hittable& h = d->hittables[i];
+        BuildItem& it = items[i];
+        it.id = i;
+        if (h.kind == RTP_HITTABLE_SPHERE) {
+            if (h.material >= d->n_materials) return set_error(RTP_ERR_INVALID, "sphere material out of range");
+            for (int k = 0; k < 3; ++k) {
+                it.bmin[k] = h.center[k] - h.radius;
+                it.bmax[k] = h.center[k] + h.radius;
+            }
+        } else if (h.kind == RTP_HITTABLE_TRIANGLE) {
+            if (h.mesh >= d->n_meshes || static_cast<uint64_t>(h.triangle) + 3 > d->meshes[h.mesh].n_indices)
+                return set_error(RTP_ERR_INVALID, "triangle id out of range");
+            const rtp_mesh& m = d->meshes[h.mesh];
+            const double* a = m.vertices[m.indices[h.triangle + 0]].position;
+            const double* b = m.vertices[m.indices[h.triangle + 1]].position;
+            const double* c = m.vertices[m.indices[h.triangle + 2]].position;
+            for (int k = 0; k < 3; ++k) {
+                it.bmin[k] = min_num(min_num(a[k], b[k]), c[k]);
+                it.bmax[k] = max_num(max_num(a[k], b[k]), c[k]);
+            }
+        } else {
+            return set_error(RTP_ERR_UNSUPPORTED, "nested List/Bvh hittables are outside the hot path (DESIGN.md)");
+        }
+        if (d->root_kind == RTP_ROOT_BVH)
+            for (int k = 0; k < 3; ++k) {
+                double key = 0.5 * (it.bmin[k] + it.bmax[k]);
+                if (key != key)  // partial_cmp().unwrap() panics on NaN (bvh.rs:63)
+                    return set_error(RTP_ERR_INVALID, "NaN bounding-box centroid in hittable " + std::to_string(i));
+            }
+    }
+
+    // ---- tree ---------------------------------------------------------------------------------
+    out->depth = 0;
+    if (d->root_kind == RTP_ROOT_BVH) {
+        out->nodes.assign(static_cast<size_t>(2) * n - 1, DNode{});
+        Builder b{items, out->nodes};
+        b.build(0, n, 0, 0, 1, 4);
+        out->depth = b.depth.load();
+    }
+    // List roots keep the caller's order (hittable.rs:113); Bvh roots are now in DFS-rank order.
+
+    // ---- primitives in traversal order ----------------------------------------------------------
+    out->prims.resize(n);
+    out->attrs.resize(n);
+    out->leaf_order.resize(n);
+    for (uint32_t slot = 0; slot < n; ++slot) {
+        uint32_t id = items[slot].id;
+        const rtp_hittable& h = d->hittables[id];
+        DPrim& p = out->prims[slot];
+        DAttr& at = out->attrs[slot];
+        std::memset(&p, 0, sizeof p);
+        std::memset(&at, 0, sizeof at);
+        p.leaf = id;
+        out->leaf_order[slot] = id;
+        if (h.kind == RTP_HITTABLE_SPHERE) {
+            for (int k = 0; k < 3; ++k) p.a[k] = h.center[k];
+            p.ba[0] = h.radius;
+            p.material = h.material;
+        } else {
+            const rtp_mesh& m = d->meshes[h.mesh];
+            const rtp_vertex& va = m.vertices[m.indices[h.triangle + 0]];
+            const rtp_vertex& vb = m.vertices[m.indices[h.triangle + 1]];
+            const rtp_vertex& vc = m.vertices[m.indices[h.triangle + 2]];
+            for (int k = 0; k < 3; ++k) {
+                p.a[k] = va.position[k];
+                p.ba[k] = va.position[k] - vb.position[k];  // hittable.rs:71
+                p.ca[k] = va.position[k] - vc.position[k];  // hittable.rs:72
+                at.n[0][k] = va.normal[k];
+                at.n[1][k] = vb.normal[k];
+                at.n[2][k] = vc.normal[k];
+            }
+            for (int k = 0; k < 2; ++k) {
+                at.uv[0][k] = va.uv[k];
+                at.uv[1][k] = vb.uv[k];
+                at.uv[2][k] = vc.uv[k];
+            }
+            p.material = m.material;  // hittable.rs:107
+        }
+    }
+    if (d->root_kind == RTP_ROOT_BVH) {
+        for (DNode& nd : out->nodes)
+            if (nd.prim != kNoPrim) nd.kind = d->hittables[items[nd.prim].id].kind;
+    } else {
+        // a List root is traversed as a flat run of leaves without slab tests; nodes carry only the kind
+        out->nodes.assign(n ? n : 1, DNode{});
+        for (uint32_t slot = 0; slot < n; ++slot) {
+            DNode& nd = out->nodes[slot];
+            nd.skip = slot + 1; nd.prim = slot; nd.kind = d->hittables[slot].kind;
+        }
+        if (n == 0) { out->nodes[0].skip = 1; out->nodes[0].prim = kNoPrim; }
+    }
+    return RTP_OK;
+}
+
+// --------------------------------------------------------------------------- OBJ -----------------
+
+namespace {
+
+struct ObjCorner {
+    uint32_t p, n, t;  // n, t == RTP_MISS when absent
+    bool operator==(const ObjCorner& o) const { return p == o.p && n == o.n && t == o.t; }
+};
+struct ObjCornerHash {
+    size_t operator()(const ObjCorner& c) const {
+        uint64_t h = c.p * 0x9E3779B97F4A7C15ull;
+        h ^= (h >> 29) + c.n * 0xBF58476D1CE4E5B9ull;
+        h ^= (h >> 31) + c.t * 0x94D049BB133111EBull;
+        return static_cast<size_t>(h ^ (h >> 32));
+    }
+};
+
+struct Cursor {
+    const char* p;
+    const char* end;
+    bool blank() const { return p < end && (*p == ' ' || *p == '\t'); }
+    // nom `space1`
+    bool space1() {
+        if (!blank()) return false;
+        while (blank()) ++p;
+        return true;
+    }
+    // nom `double`: no leading whitespace allowed
+    bool real(double* out) {
+        if (p >= end || blank() || *p == '\r' || *p == '\n') return false;
+        char* e = nullptr;
+        double v = std::strtod(p, &e);
+        if (e == p) return false;
+        p = e;
+        *out = v;
+        return true;
+    }
+    bool reals(double* out, int n) {
+        for (int k = 0; k < n; ++k) {
+            if (k && !space1()) return false;
+            if (!real(&out[k])) return false;
+        }
+        return true;
+    }
+    // mesh.rs:58-70: separated_list1("/", opt(integer)); [0] position (required), [1] texcoord, [2] normal
+    bool corner(ObjCorner* out) {
+        uint32_t val[3] = {0, 0, 0};
+        bool have[3] = {false, false, false};
+        const char* q = p;
+        for (int field = 0;; ++field) {
+            uint64_t v = 0;
+            int digits = 0;
+            while (q < end && *q >= '0' && *q <= '9') {
+                v = v * 10 + static_cast<uint64_t>(*q - '0');
+                if (v > 0xFFFFFFFFull) return false;
+                ++q; ++digits;
+            }
+            if (field < 3) { have[field] = digits > 0; val[field] = static_cast<uint32_t>(v); }
+            if (q < end && *q == '/') { ++q; continue; }
+            break;
+        }
+        if (!have[0]) return false;
+        out->p = val[0] - 1;
+        out->t = have[1] ? val[1] - 1 : RTP_MISS;
+        out->n = have[2] ? val[2] - 1 : RTP_MISS;
+        p = q;
+        return true;
+    }
+};
+
+}  // namespace
+
+static int obj_load(const char* path, rtp_mesh* out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return set_error(RTP_ERR_IO, std::string("cannot open ") + path);
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+
+    std::vector<double> positions, normals, texcoords;  // flat xyz / xyz / uv
+    std::vector<ObjCorner> corners;
+    std::vector<std::pair<uint32_t, uint32_t>> faces;  // first corner, corner count
+
+    const char* s = text.data();
+    const char* end = s + text.size();
+    while (s < end) {
+        const char* eol = static_cast<const char*>(std::memchr(s, '\n', static_cast<size_t>(end - s)));
+        if (!eol) eol = end;
+        Cursor c{s, eol};
+        double v[3];
+        // mesh.rs:94-101: alt((v, vn, vt, f)); each is tag + space1 + payload, unparseable lines are skipped
+        if (eol - s >= 2 && s[0] == 'v' && (s[1] == ' ' || s[1] == '\t')) {
+            c.p = s + 1;
+            if (c.space1() && c.reals(v, 3)) positions.insert(positions.end(), v, v + 3);
+        } else if (eol - s >= 3 && s[0] == 'v' && s[1] == 'n') {
+            c.p = s + 2;
+            if (c.space1() && c.reals(v, 3)) normals.insert(normals.end(), v, v + 3);
+        } else if (eol - s >= 3 && s[0] == 'v' && s[1] == 't') {
+            c.p = s + 2;
+            if (c.space1() && c.reals(v, 2)) texcoords.insert(texcoords.end(), v, v + 2);
+        } else if (eol - s >= 2 && s[0] == 'f') {
+            c.p = s + 1;
+            if (c.space1()) {
+                uint32_t first = static_cast<uint32_t>(corners.size()), count = 0;
+                ObjCorner oc;
+                while (c.corner(&oc)) {
+                    corners.push_back(oc);
+                    ++count;
+                    if (!c.space1()) break;
+                }
+                if (count) faces.emplace_back(first, count);
+            }
+        }
+        s = eol + 1;
+    }
+
+    // mesh.rs:151-166: one vertex per distinct (p, n, t), numbered in first-seen order
+    std::unordered_map<ObjCorner, uint32_t, ObjCornerHash> unique;
+    unique.reserve(corners.size());
+    std::vector<rtp_vertex> vertices;
+    std::vector<uint32_t> corner_vertex(corners.size());
+    const size_t np = positions.size() / 3, nn = normals.size() / 3, nt = texcoords.size() / 2;
+    for (size_t k = 0; k < corners.size(); ++k) {
+        const ObjCorner& oc = corners[k];
+        auto it = unique.find(oc);
+        if (it != unique.end()) { corner_vertex[k] = it->second; continue; }
+        if (oc.p >= np || (oc.n != RTP_MISS && oc.n >= nn) || (oc.t != RTP_MISS && oc.t >= nt))
+            return set_error(RTP_ERR_FORMAT, "obj index out of range (the reference panics here)");
+        rtp_vertex vx;
+        std::memset(&vx, 0, sizeof vx);  // DEFAULT_NORMAL / DEFAULT_UV are zero (mesh.rs:146-147)
+        std::memcpy(vx.position, &positions[3 * oc.p], 24);
+        if (oc.n != RTP_MISS) std::memcpy(vx.normal, &normals[3 * oc.n], 24);
+        if (oc.t != RTP_MISS) std::memcpy(vx.uv, &texcoords[2 * oc.t], 16);
+        uint32_t id = static_cast<uint32_t>(vertices.size());
+        unique.emplace(oc, id);
+        vertices.push_back(vx);
+        corner_vertex[k] = id;
+    }
+    std::vector<uint32_t> indices;
+    indices.reserve(faces.size() * 3);
+    for (const auto& fc : faces) {  // mesh.rs:169-179
+        if (fc.second != 3) return set_error(RTP_ERR_FORMAT, "Non-triangular face are not supported");
+        for (uint32_t k = 0; k < 3; ++k) indices.push_back(corner_vertex[fc.first + k]);
+    }
+
+    auto* vout = static_cast<rtp_vertex*>(std::malloc(sizeof(rtp_vertex) * std::max<size_t>(vertices.size(), 1)));
+    auto* iout = static_cast<uint32_t*>(std::malloc(sizeof(uint32_t) * std::max<size_t>(indices.size(), 1)));
+    if (!vout || !iout) { std::free(vout); std::free(iout); return set_error(RTP_ERR_NOMEM, "out of memory"); }
+    if (!vertices.empty()) std::memcpy(vout, vertices.data(), sizeof(rtp_vertex) * vertices.size());
+    if (!indices.empty()) std::memcpy(iout, indices.data(), sizeof(uint32_t) * indices.size());
+    out->vertices = vout;
+    out->indices = iout;
+    out->n_vertices = static_cast<uint32_t>(vertices.size());
+    out->n_indices = static_cast<uint32_t>(indices.size());
+    out->material = 0;  // mesh.rs:181
+    out->_pad = 0;
+    return RTP_OK;
+}
+
+// --------------------------------------------------------------------------- TGA -----------------
+
+static int tga_load(const char* path, rtp_image* out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return set_error(RTP_ERR_IO, std::string("cannot open ") + path);
+    unsigned char hd[18];
+    if (!f.read(reinterpret_cast<char*>(hd), 18)) return set_error(RTP_ERR_IO, "truncated tga header");
+    const uint32_t w = hd[12] | (hd[13] << 8), h = hd[14] | (hd[15] << 8);
+    const unsigned bpp = hd[16];
+    const bool flip = (hd[17] & (1u << 5)) != 0;  // image.rs:95-99
+    if (hd[0] != 0 || hd[1] != 0 || hd[2] != 2 || (bpp != 24 && bpp != 32))  // image.rs:81-88
+        return set_error(RTP_ERR_FORMAT, "This tga header is not supported");
+    const size_t src_px = bpp / 8, n = static_cast<size_t>(w) * h;
+    std::vector<unsigned char> raw(n * src_px);
+    if (n && !f.read(reinterpret_cast<char*>(raw.data()), static_cast<std::streamsize>(raw.size())))
+        return set_error(RTP_ERR_IO, "truncated tga data");
+    auto* rgba = static_cast<uint8_t*>(std::malloc(std::max<size_t>(n * 4, 1)));
+    if (!rgba) return set_error(RTP_ERR_NOMEM, "out of memory");
+    for (uint32_t row = 0; row < h; ++row) {
+        const uint32_t dst_row = flip ? h - 1 - row : row;
+        const unsigned char* src = raw.data() + static_cast<size_t>(row) * w * src_px;
+        uint8_t* dst = rgba + static_cast<size_t>(dst_row) * w * 4;
+        for (uint32_t x = 0; x < w; ++x, src += src_px, dst += 4) {
+            dst[0] = src[2]; dst[1] = src[1]; dst[2] = src[0];
+            dst[3] = src_px == 4 ? src[3] : 0xff;
+        }
+    }
+    out->rgba = rgba; out->width = w; out->height = h;
+    return RTP_OK;
+}
+
+static int tga_save(const rtp_image* img, const char* path) {
+    if (img->width > 0xFFFFu || img->height > 0xFFFFu)
+        return set_error(RTP_ERR_INVALID, "image dimensions do not fit a tga header (try_into fails, image.rs:123-124)");
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return set_error(RTP_ERR_IO, std::string("cannot create ") + path);
+    unsigned char hd[18] = {0};
+    hd[2] = 2; hd[16] = 32;  // uncompressed BGRA, descriptor 0 = bottom-origin (image.rs:120-121)
+    hd[12] = img->width & 0xff; hd[13] = img->width >> 8;
+    hd[14] = img->height & 0xff; hd[15] = img->height >> 8;
+    f.write(reinterpret_cast<const char*>(hd), 18);
+    const size_t n = static_cast<size_t>(img->width) * img->height;
+    std::vector<unsigned char> bgra(n * 4);
+    for (size_t k = 0; k < n; ++k) {
+        bgra[4 * k + 0] = img->rgba[4 * k + 2];
+        bgra[4 * k + 1] = img->rgba[4 * k + 1];
+        bgra[4 * k + 2] = img->rgba[4 * k + 0];
+        bgra[4 * k + 3] = img->rgba[4 * k + 3];
+    }
+    f.write(reinterpret_cast<const char*>(bgra.data()), static_cast<std::streamsize>(bgra.size()));
+    if (!f) return set_error(RTP_ERR_IO, "short write");
+    return RTP_OK;
+}
+
+// --------------------------------------------------------------------------- Philox --------------
+
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t m0 = 0xD2511F53ull * c[0], m1 = 0xCD9E8D57ull * c[2];
+        const uint32_t x0 = static_cast<uint32_t>(m1 >> 32) ^ c[1] ^ k0;
+        const uint32_t x2 = static_cast<uint32_t>(m0 >> 32) ^ c[3] ^ k1;
+        c[0] = x0; c[1] = static_cast<uint32_t>(m1); c[2] = x2; c[3] = static_cast<uint32_t>(m0);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+}  // namespace rtp
+
+// =============================================================================================
+// C ABI — host-only entry points
+// =============================================================================================
+
+using namespace rtp;
+
+extern "C" {
+
+const char* rtp_last_error(void) { return g_last_error.c_str(); }
+uint32_t rtp_abi_version(void) { return RTP_ABI_VERSION; }
+
+int rtp_obj_load(const char* path, rtp_mesh* out) {
+    if (!path || !out) return set_error(RTP_ERR_INVALID, "null argument");
+    try { return obj_load(path, out); } catch (const std::exception& e) { return set_error(RTP_ERR_NOMEM, e.what()); }
+}
+
+void rtp_mesh_free(rtp_mesh* mesh) {
+    if (!mesh) return;
+    std::free(const_cast<rtp_vertex*>(mesh->vertices));
+    std::free(const_cast<uint32_t*>(mesh->indices));
+    mesh->vertices = nullptr; mesh->indices = nullptr;
+    mesh->n_vertices = mesh->n_indices = 0;
+}
+
+int rtp_tga_load(const char* path, rtp_image* out) {
+    if (!path || !out) return set_error(RTP_ERR_INVALID, "null argument");
+    try { return tga_load(path, out); } catch (const std::exception& e) { return set_error(RTP_ERR_NOMEM, e.what()); }
+}
+
+int rtp_tga_save(const rtp_image* image, const char* path) {
+    if (!image || !path || !image->rgba) return set_error(RTP_ERR_INVALID, "null argument");
+    try { return tga_save(image, path); } catch (const std::exception& e) { return set_error(RTP_ERR_NOMEM, e.what()); }
+}
+
+void rtp_image_free(rtp_image* image) {
+    if (!image) return;
+    std::free(image->rgba);
+    image->rgba = nullptr; image->width = image->height = 0;
+}
+
+int rtp_camera_lookat(const double position[3], const double target[3], const double up[3], rtp_camera* cam) {
+    if (!position || !target || !up || !cam) return set_error(RTP_ERR_INVALID, "null argument");
+    // utility.rs:172-177
+    double d[3] = {position[0] - target[0], position[1] - target[1], position[2] - target[2]};
+    const double len = std::sqrt(0.0 + dot3(d, d));
+    const double z[3] = {d[0] / len, d[1] / len, d[2] / len};
+    const double x[3] = {up[1] * z[2] - up[2] * z[1], up[2] * z[0] - up[0] * z[2], up[0] * z[1] - up[1] * z[0]};
+    const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+    for (int r = 0; r < 3; ++r) {
+        cam->orientation[0 + r] = x[r];
+        cam->orientation[3 + r] = y[r];
+        cam->orientation[6 + r] = z[r];
+        cam->position[r] = position[r];
+    }
+    return RTP_OK;
+}
+
+int rtp_frame_to_srgb8(const double* rgb, uint32_t width, uint32_t height, uint8_t* out) {
+    if (!rgb || !out) return set_error(RTP_ERR_INVALID, "null argument");
+    const size_t n = static_cast<size_t>(width) * height;
+    for (size_t p = 0; p < n; ++p) {
+        for (int k = 0; k < 3; ++k) {  // utility.rs:212-220
+            double x = rgb[3 * p + k];
+            x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);  // f64::clamp keeps NaN
+            const double y = 255.0 * std::pow(x, 1.0 / 2.2);
+            out[4 * p + k] = !(y == y) || y <= 0.0 ? 0 : (y >= 255.0 ? 255 : static_cast<uint8_t>(y));  // `as u8` saturates
+        }
+        out[4 * p + 3] = 0xff;
+    }
+    return RTP_OK;
+}
+
+int rtp_split_in_tiles(uint32_t fw, uint32_t fh, uint32_t tw, uint32_t th, uint32_t* tiles, size_t cap, size_t* n) {
+    if (!n || tw == 0 || th == 0) return set_error(RTP_ERR_INVALID, "bad tile arguments");
+    // image.rs:151-167
+    const uint32_t nti = (fw + tw - 1) / tw, ntj = (fh + th - 1) / th;
+    size_t count = 0;
+    for (uint32_t tj = 0; tj < ntj; ++tj)
+        for (uint32_t ti = 0; ti < nti; ++ti, ++count) {
+            if (!tiles || count >= cap) continue;
+            const uint32_t oi = ti * tw, oj = tj * th;
+            tiles[4 * count + 0] = oi;
+            tiles[4 * count + 1] = oj;
+            tiles[4 * count + 2] = std::min(tw, fw - oi);
+            tiles[4 * count + 3] = std::min(th, fh - oj);
+        }
+    *n = count;
+    return RTP_OK;
+}
+
+int rtp_rng_draws(uint64_t seed, uint32_t index_lo, uint32_t index_hi, uint32_t stream, uint32_t first_draw,
+                  uint32_t n_draws, double* out) {
+    if (n_draws && !out) return set_error(RTP_ERR_INVALID, "null argument");
+    uint32_t cached = 0xFFFFFFFFu, block[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < n_draws; ++i) {
+        const uint32_t k = first_draw + i, b = k >> 1, pair = k & 1u;
+        if (b != cached) {
+            block[0] = index_lo; block[1] = index_hi; block[2] = b; block[3] = stream;
+            philox4x32_10(block, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+            cached = b;
+        }
+        const uint64_t u = (static_cast<uint64_t>(block[2 * pair + 1]) << 32) | block[2 * pair];
+        out[i] = static_cast<double>(u >> 11) * 0x1.0p-53;
+    }
+    return RTP_OK;
+}
+
+}  // extern "C"

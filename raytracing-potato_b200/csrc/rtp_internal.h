@@ -1,0 +1,124 @@
+// rtp_internal.h — structures shared by the host layer (rtp_host.cpp) and the device layer
+// (rtp_device.cu). Not part of the ABI.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rtp.h"
+
+namespace rtp {
+
+// ---------------------------------------------------------------------------------------------
+// Device layout (HBM). All records are 16-byte aligned so they load as 128-bit vectors.
+//
+// Nodes are stored in the reference's depth-first, left-before-right order (pre-order), so the
+// reference traversal bvh.rs:93-119 becomes a stack-free walk: a node that passes its slab test
+// is followed by node+1 (its left child, or for a leaf simply the next subtree), a node that
+// fails jumps to `skip`, the first pre-order index after its subtree.
+// ---------------------------------------------------------------------------------------------
+
+constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
+
+struct alignas(64) DNode {  // 64 B
+    double bmin[3];
+    double bmax[3];
+    uint32_t skip;  // pre-order index of the next node once this subtree is done
+    uint32_t prim;  // leaf: primitive slot (= DFS rank of the leaf); branch: kNoPrim
+    uint32_t kind;  // leaf: rtp_hittable_kind
+    uint32_t _pad;
+};
+static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
+
+// One primitive per leaf (bvh.rs:43-47), stored in DFS-rank order so a traversal touches them
+// in increasing address order. Triangle: a, ba = a-b, ca = a-c precomputed on the host with the
+// same IEEE subtraction the reference performs per test (hittable.rs:71-72) — bit-identical.
+// Sphere: center in a[], radius in ba[0].
+struct alignas(16) DPrim {  // 80 B
+    double a[3];
+    double ba[3];
+    double ca[3];
+    uint32_t leaf;      // LeafId handed back to the caller
+    uint32_t material;  // MaterialId
+};
+static_assert(sizeof(DPrim) == 80, "DPrim must be 80 bytes");
+
+// Shading attributes of a triangle (mesh.rs:7-11 normals/uvs of its three vertices), read once
+// per accepted path vertex, never during traversal.
+struct alignas(16) DAttr {  // 128 B; uv first so that both arrays start 16-byte aligned
+    double uv[3][2];
+    double n[3][3];
+    double _pad;
+};
+static_assert(sizeof(DAttr) == 128, "DAttr must be 128 bytes");
+
+struct DTexture {
+    uint32_t kind;
+    uint32_t width, height;
+    uint32_t odd, even;
+    uint32_t _pad;
+    int64_t seed;
+    double rgb[3];
+    const uint8_t* rgba;  // device pointer
+};
+
+struct DMaterial {
+    uint32_t scatter, absorb, absorb_texture, emit_kind;
+    uint32_t emit_texture, _pad[3];
+    double scatter_param;
+    double absorb_rgb[3];
+    double emit_rgb[3];
+};
+
+struct DSceneView {  // passed by value to kernels
+    const DNode* nodes;
+    const DPrim* prims;
+    const DAttr* attrs;
+    const DMaterial* materials;
+    const DTexture* textures;
+    uint32_t n_nodes;
+    uint32_t n_prims;
+    uint32_t root_kind;
+    uint32_t bg_kind;
+    uint32_t bg_texture;
+    uint32_t _pad;
+    double bg_rgb[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Host-side flattened scene produced by rtp_host.cpp and uploaded by rtp_device.cu
+// ---------------------------------------------------------------------------------------------
+struct FlatScene {
+    std::vector<DNode> nodes;
+    std::vector<DPrim> prims;
+    std::vector<DAttr> attrs;
+    std::vector<DMaterial> materials;
+    std::vector<DTexture> textures;            // rgba = nullptr here; filled at upload
+    std::vector<std::vector<uint8_t>> images;  // per texture (empty unless Image)
+    std::vector<uint32_t> leaf_order;          // LeafId by DFS rank
+    uint32_t root_kind = 0;
+    uint32_t depth = 0;
+    rtp_emit background{};
+};
+
+// error plumbing (rtp_host.cpp)
+int set_error(int code, const std::string& msg);
+
+// host layer
+int flatten_scene(const rtp_scene_desc* desc, FlatScene* out);
+
+// device layer (rtp_device.cu)
+struct DeviceScene;
+int device_scene_upload(const FlatScene& flat, DeviceScene** out);
+void device_scene_free(DeviceScene* ds);
+uint64_t device_scene_bytes(const DeviceScene* ds);
+
+}  // namespace rtp
+
+struct rtp_scene {
+    rtp::FlatScene flat;  // nodes/prims/attrs are released after upload; leaf_order is kept
+    rtp::DeviceScene* dev = nullptr;
+    uint32_t n_leaves = 0, n_nodes = 0;
+};
