@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -244,6 +245,64 @@ __device__ __forceinline__ void finish_sphere(const DSceneView& sc, const HitRec
 // kernels: ray batches
 // ---------------------------------------------------------------------------------------------
 
+template <bool FULL>
+__device__ __forceinline__ void write_hit(const DSceneView& sc, void* __restrict__ out, size_t i, D3 o, D3 d, const HitRec& h) {
+    if (FULL) {
+        rtp_hit_full* o_full = static_cast<rtp_hit_full*>(out) + i;
+        rtp_hit_full r;
+        if (h.slot != kNoPrim) {
+            Surface s;
+            finish_hit(sc, o, d, h, s);
+            if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
+            else finish_sphere(sc, h, s);
+            r.leaf = s.leaf; r.material = s.material; r.t = h.t;
+            r.position[0] = s.position.x; r.position[1] = s.position.y; r.position[2] = s.position.z;
+            r.normal[0] = s.normal.x; r.normal[1] = s.normal.y; r.normal[2] = s.normal.z;
+            r.uv[0] = s.u; r.uv[1] = s.v;
+        } else {
+            memset(&r, 0, sizeof r);
+            r.leaf = RTP_MISS; r.material = RTP_MISS; r.t = CUDART_INF;
+        }
+        *o_full = r;
+    } else {
+        uint4 w;
+        if (h.slot != kNoPrim) {
+            const DPrim* p = sc.prims + h.slot;
+            w.x = __ldg(&p->leaf); w.y = __ldg(&p->material);
+            const unsigned long long tb = static_cast<unsigned long long>(__double_as_longlong(h.t));
+            w.z = static_cast<uint32_t>(tb); w.w = static_cast<uint32_t>(tb >> 32);
+        } else {
+            w.x = RTP_MISS; w.y = RTP_MISS;
+            w.z = 0u; w.w = 0x7FF00000u;  // +inf
+        }
+        reinterpret_cast<uint4*>(out)[i] = w;
+    }
+}
+
+// one atomic per warp per counter
+template <bool COUNT>
+__device__ __forceinline__ void flush_counters(Counters* counters, const LocalCounters& lc) {
+    if (!counters) return;
+    unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests;
+    for (int off = 16; off; off >>= 1) {
+        r += __shfl_down_sync(0xffffffffu, r, off);
+        if (COUNT) {
+            nv += __shfl_down_sync(0xffffffffu, nv, off);
+            tt += __shfl_down_sync(0xffffffffu, tt, off);
+            st += __shfl_down_sync(0xffffffffu, st, off);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counters->rays, static_cast<unsigned long long>(r));
+        if (COUNT) {
+            atomicAdd(&counters->node_visits, static_cast<unsigned long long>(nv));
+            atomicAdd(&counters->triangle_tests, static_cast<unsigned long long>(tt));
+            atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
+        }
+    }
+}
+
+// Baseline kernel: one thread per ray, no regrouping. Kept for A/B runs (RTP_TRACE_KERNEL=simple).
 template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                             Counters* counters) {
@@ -256,55 +315,140 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const
         HitRec h;
         h.t = r3.y; h.u = 0.0; h.v = 0.0; h.kind = 0;
         closest_hit<COUNT>(sc, o, d, r3.x, h, lc);
-        if (FULL) {
-            rtp_hit_full* o_full = static_cast<rtp_hit_full*>(out) + i;
-            rtp_hit_full r;
-            if (h.slot != kNoPrim) {
-                Surface s;
-                finish_hit(sc, o, d, h, s);
-                if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
-                else finish_sphere(sc, h, s);
-                r.leaf = s.leaf; r.material = s.material; r.t = h.t;
-                r.position[0] = s.position.x; r.position[1] = s.position.y; r.position[2] = s.position.z;
-                r.normal[0] = s.normal.x; r.normal[1] = s.normal.y; r.normal[2] = s.normal.z;
-                r.uv[0] = s.u; r.uv[1] = s.v;
-            } else {
-                memset(&r, 0, sizeof r);
-                r.leaf = RTP_MISS; r.material = RTP_MISS; r.t = CUDART_INF;
+        write_hit<FULL>(sc, out, i, o, d, h);
+    }
+    flush_counters<COUNT>(counters, lc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent wavefront traversal. One warp owns 32 ray slots and keeps them busy:
+//   * lanes whose ray has finished pull new ray indices from a global counter (one atomic per
+//     refill, ranks by ballot), so a warp never idles behind its longest ray;
+//   * lanes that reach a leaf whose slab gate passes park until enough lanes are parked, then
+//     the primitive tests run together (ballot-batched), so the expensive triangle/sphere code
+//     is not executed for one lane at a time.
+// Every lane still performs exactly the reference's sequence of tests for its ray (pre-order
+// walk, bvh.rs:93-119), so results are independent of how rays are grouped.
+// ---------------------------------------------------------------------------------------------
+
+struct WorkQueue {
+    unsigned long long next;   // next unclaimed ray index
+    unsigned int done_blocks;  // blocks that have drained; the last one resets the queue for the next launch
+    unsigned int _pad;
+};
+
+constexpr int kRefillMin = 8;   // refill when at least this many lanes are empty
+constexpr int kPrimBatch = 8;   // run primitive tests when at least this many lanes are parked at a leaf
+
+enum LaneState : int { LANE_EMPTY = 0, LANE_WALK = 1, LANE_PRIM = 2 };
+
+template <bool COUNT, bool FULL>
+__global__ void __launch_bounds__(128, 4) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+                                                                  Counters* counters, WorkQueue* wq) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const DNode* __restrict__ nodes = sc.nodes;
+    const uint32_t n_nodes = sc.n_nodes;
+    const bool is_list = sc.root_kind != RTP_ROOT_BVH;
+    const uint32_t n_steps_end = is_list ? sc.n_prims : n_nodes;  // List roots walk the primitive run without slab gates
+    LocalCounters lc = {0, 0, 0, 0};
+
+    D3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
+    double tmin = 0.0;
+    HitRec h;
+    h.t = 0.0; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
+    uint32_t node = 0, prim = kNoPrim, kind = 0;
+    size_t idx = 0;
+    int state = LANE_EMPTY;
+    bool more = true;  // warp-uniform: the queue may still hold rays
+
+    for (;;) {
+        // ---- refill -------------------------------------------------------------------------------
+        const unsigned empty = __ballot_sync(0xffffffffu, state == LANE_EMPTY);
+        if (empty == 0xffffffffu || (more && __popc(empty) >= kRefillMin)) {
+            if (more) {
+                const int cnt = __popc(empty), leader = __ffs(empty) - 1;
+                unsigned long long base = 0;
+                if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (state == LANE_EMPTY) {
+                    idx = static_cast<size_t>(base) + __popc(empty & lt_mask);
+                    if (idx < n) {
+                        const double2* rp = reinterpret_cast<const double2*>(rays + idx);
+                        const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+                        o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
+                        inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
+                        tmin = r3.x;
+                        h.t = r3.y; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
+                        node = 0;
+                        state = LANE_WALK;
+                        lc.rays++;
+                    }
+                }
+                if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
             }
-            *o_full = r;
-        } else {
-            uint4 w;
-            if (h.slot != kNoPrim) {
-                const DPrim* p = sc.prims + h.slot;
-                w.x = __ldg(&p->leaf); w.y = __ldg(&p->material);
-                const unsigned long long tb = static_cast<unsigned long long>(__double_as_longlong(h.t));
-                w.z = static_cast<uint32_t>(tb); w.w = static_cast<uint32_t>(tb >> 32);
-            } else {
-                w.x = RTP_MISS; w.y = RTP_MISS;
-                w.z = 0u; w.w = 0x7FF00000u;  // +inf
+            if (__ballot_sync(0xffffffffu, state != LANE_EMPTY) == 0u) {
+                if (!more) break;
+                continue;
             }
-            reinterpret_cast<uint4*>(out)[i] = w;
+        }
+
+        // ---- walk: every walking lane visits one node per iteration -------------------------------
+        for (;;) {
+            if (state == LANE_WALK) {
+                if (node >= n_steps_end) {
+                    write_hit<FULL>(sc, out, idx, o, d, h);
+                    state = LANE_EMPTY;
+                } else if (is_list) {
+                    prim = node; kind = __ldg(&nodes[node].kind);
+                    node = node + 1;
+                    state = LANE_PRIM;
+                } else {
+                    const double* nb = nodes[node].bmin;
+                    const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
+                    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
+                    if (COUNT) lc.node_visits++;
+                    if (collide_literal(b0, b1, b2, o, inv, tmin, h.t)) {
+                        node = node + 1;
+                        if (meta.y != kNoPrim) { prim = meta.y; kind = meta.z; state = LANE_PRIM; }
+                    } else {
+                        node = meta.x;
+                    }
+                }
+            }
+            const unsigned walking = __ballot_sync(0xffffffffu, state == LANE_WALK);
+            if (walking == 0u) break;
+            const unsigned parked = __ballot_sync(0xffffffffu, state == LANE_PRIM);
+            if (__popc(parked) >= kPrimBatch) break;
+            if (more && __popc(~(walking | parked)) >= kRefillMin) break;
+        }
+
+        // ---- primitive tests for the parked lanes ------------------------------------------------
+        if (state == LANE_PRIM) {
+            const DPrim* p = sc.prims + prim;
+            double t, u = 0.0, v = 0.0;
+            bool hit;
+            if (kind == RTP_HITTABLE_TRIANGLE) {
+                if (COUNT) lc.triangle_tests++;
+                hit = test_triangle(p, o, d, tmin, h.t, t, u, v);
+            } else {
+                if (COUNT) lc.sphere_tests++;
+                hit = test_sphere(p, o, d, tmin, h.t, t);
+            }
+            if (hit) { h.t = t; h.u = u; h.v = v; h.slot = prim; h.kind = kind; }
+            state = LANE_WALK;
         }
     }
-    if (counters) {
-        // one atomic per warp per counter
-        unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests;
-        for (int off = 16; off; off >>= 1) {
-            r += __shfl_down_sync(0xffffffffu, r, off);
-            if (COUNT) {
-                nv += __shfl_down_sync(0xffffffffu, nv, off);
-                tt += __shfl_down_sync(0xffffffffu, tt, off);
-                st += __shfl_down_sync(0xffffffffu, st, off);
-            }
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&counters->rays, static_cast<unsigned long long>(r));
-            if (COUNT) {
-                atomicAdd(&counters->node_visits, static_cast<unsigned long long>(nv));
-                atomicAdd(&counters->triangle_tests, static_cast<unsigned long long>(tt));
-                atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
-            }
+
+    flush_counters<COUNT>(counters, lc);
+    // the last block to drain rearms the queue, so back-to-back launches need no memset
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&wq->done_blocks, 1u) == gridDim.x - 1) {
+            wq->next = 0ull;
+            wq->done_blocks = 0u;
+            __threadfence();
         }
     }
 }
@@ -643,25 +787,7 @@ __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamer
         }
         scratch[p] = make_double4(L.x, L.y, L.z, first_hit ? 1.0 : 0.0);
     }
-    if (counters) {
-        unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests;
-        for (int off = 16; off; off >>= 1) {
-            r += __shfl_down_sync(0xffffffffu, r, off);
-            if (COUNT) {
-                nv += __shfl_down_sync(0xffffffffu, nv, off);
-                tt += __shfl_down_sync(0xffffffffu, tt, off);
-                st += __shfl_down_sync(0xffffffffu, st, off);
-            }
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&counters->rays, static_cast<unsigned long long>(r));
-            if (COUNT) {
-                atomicAdd(&counters->node_visits, static_cast<unsigned long long>(nv));
-                atomicAdd(&counters->triangle_tests, static_cast<unsigned long long>(tt));
-                atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
-            }
-        }
-    }
+    flush_counters<COUNT>(counters, lc);
 }
 
 // main.rs:78-87: per pixel, add the samples of this launch in sample order to the running sums; on the
@@ -697,6 +823,7 @@ __global__ void __launch_bounds__(256) write_frame_kernel(const double4* __restr
 // ---------------------------------------------------------------------------------------------
 
 constexpr int kPipeDepth = 3;
+constexpr unsigned kQueueSlots = 64;
 constexpr size_t kChunkRays = 1u << 18;  // 16 MiB of rays per pipeline stage
 
 struct DeviceScene {
@@ -712,6 +839,10 @@ struct DeviceScene {
 
     std::mutex lock;  // serialises calls that use the scratch below
     Counters* counters = nullptr;
+    WorkQueue* queues = nullptr;       // kQueueSlots self-rearming work queues, handed out round-robin per launch
+    unsigned queue_seq = 0;
+    int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
+    bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
@@ -735,6 +866,7 @@ void device_scene_free(DeviceScene* ds) {
     cudaFree(ds->nodes); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
     for (uint8_t* p : ds->images) cudaFree(p);
     cudaFree(ds->counters);
+    cudaFree(ds->queues);
     for (int k = 0; k < kPipeDepth; ++k) {
         if (ds->streams[k]) cudaStreamDestroy(ds->streams[k]);
         cudaFree(ds->stage_rays[k]); cudaFree(ds->stage_hits[k]);
@@ -776,6 +908,17 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     }
     if ((rc = upload(tex, &ds->textures, &ds->bytes)) != RTP_OK) return bail(rc);
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ds->counters), sizeof(Counters));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ds->queues), kQueueSlots * sizeof(WorkQueue));
+    if (e == cudaSuccess) e = cudaMemset(ds->queues, 0, kQueueSlots * sizeof(WorkQueue));
+    if (e == cudaSuccess) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, ds->device);
+        int per_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, false>, 128, 0);
+        ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
+        const char* env = std::getenv("RTP_TRACE_KERNEL");
+        ds->use_simple_kernel = env && std::string(env) == "simple";
+    }
     for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_end);
@@ -805,15 +948,29 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
                         cudaStream_t stream) {
     if (n == 0) return RTP_OK;
     const unsigned block = 128;
-    const size_t grid = (n + block - 1) / block;
-    if (grid > 0x7FFFFFFFull) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
-    const dim3 g(static_cast<unsigned>(grid));
-    if (full) {
-        if (count) trace_closest_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
-        else trace_closest_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+    if (ds->use_simple_kernel) {
+        const size_t grid = (n + block - 1) / block;
+        if (grid > 0x7FFFFFFFull) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
+        const dim3 g(static_cast<unsigned>(grid));
+        if (full) {
+            if (count) trace_closest_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+            else trace_closest_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+        } else {
+            if (count) trace_closest_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+            else trace_closest_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+        }
     } else {
-        if (count) trace_closest_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
-        else trace_closest_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
+        // persistent grid: a whole number of resident blocks per SM, never more blocks than there are warps of work
+        const size_t want = (n + block - 1) / block;
+        const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->persistent_blocks), want)));
+        WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
+        if (full) {
+            if (count) trace_persistent_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
+            else trace_persistent_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
+        } else {
+            if (count) trace_persistent_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
+            else trace_persistent_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
+        }
     }
     RTP_CUDA(cudaGetLastError());
     return RTP_OK;
