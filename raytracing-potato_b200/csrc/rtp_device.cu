@@ -88,6 +88,38 @@ __device__ __forceinline__ bool collide_literal(const double2 b0, const double2 
     return t_max >= t_min;
 }
 
+// Same decision as collide_literal for rays whose origin is finite, whose 1/direction is finite and non-zero on all
+// three axes, and whose t_min <= t_max are not NaN (no NaN can then appear in any lane):
+//   * IEEE rounding is monotone, so for inv > 0: (min-o)*inv <= (max-o)*inv and min(t0,t1) is the min-plane value; for
+//     inv < 0 it is the max-plane value. Picking the plane by the sign of inv replaces the six inner min/max, and
+//     far_a >= near_a holds on every axis.
+//   * without NaNs, min(T,fx,fy,fz) >= max(tmin,nx,ny,nz) is the conjunction of the pairwise comparisons; the four that
+//     are always true (T >= tmin is kept true by the caller, far_a >= near_a) are dropped, leaving twelve.
+// No value is selected, so the decision is a pure predicate chain. Other rays use collide_literal.
+__device__ __forceinline__ bool collide_fast(const double2 b0, const double2 b1, const double2 b2, D3 o, D3 inv, bool sx, bool sy, bool sz,
+                                             double tmin, double T) {
+    const double pnx = sx ? b1.y : b0.x, pfx = sx ? b0.x : b1.y;
+    const double pny = sy ? b2.x : b0.y, pfy = sy ? b0.y : b2.x;
+    const double pnz = sz ? b2.y : b1.x, pfz = sz ? b1.x : b2.y;
+    const double nx = (pnx - o.x) * inv.x, ny = (pny - o.y) * inv.y, nz = (pnz - o.z) * inv.z;
+    const double fx = (pfx - o.x) * inv.x, fy = (pfy - o.y) * inv.y, fz = (pfz - o.z) * inv.z;
+    const bool p0 = (T >= nx) & (T >= ny) & (T >= nz);
+    const bool p1 = (fx >= tmin) & (fx >= ny) & (fx >= nz);
+    const bool p2 = (fy >= tmin) & (fy >= nx) & (fy >= nz);
+    const bool p3 = (fz >= tmin) & (fz >= nx) & (fz >= ny);
+    return p0 & p1 & p2 & p3;
+}
+
+// out-of-line literal test for the rare rays that are not eligible for collide_fast (keeps the hot loop small)
+__device__ __noinline__ bool collide_literal_slow(const DNode* __restrict__ node, double ox, double oy, double oz, double ix, double iy, double iz,
+                                                  double tmin, double T) {
+    const double* nb = node->bmin;
+    return collide_literal(ldg2(nb), ldg2(nb + 2), ldg2(nb + 4), mk(ox, oy, oz), mk(ix, iy, iz), tmin, T);
+}
+
+__device__ __forceinline__ bool finite_nonzero(double x) { return x != 0.0 && fabs(x) <= 1.7976931348623157e308; }
+__device__ __forceinline__ bool finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
 // hittable.rs:65-108 hit_triangle up to the accept test
 __device__ __forceinline__ bool test_triangle(const DPrim* __restrict__ p, D3 o, D3 d, double ray_tmin, double ray_tmax, double& t_out,
                                               double& u_out, double& v_out) {
@@ -337,94 +369,97 @@ struct WorkQueue {
     unsigned int _pad;
 };
 
-constexpr int kRefillMin = 8;   // refill when at least this many lanes are empty
-constexpr int kPrimBatch = 8;   // run primitive tests when at least this many lanes are parked at a leaf
-
-enum LaneState : int { LANE_EMPTY = 0, LANE_WALK = 1, LANE_PRIM = 2 };
+struct Tuning {
+    int refill_min;  // refill when at least this many lanes are empty
+    int prim_batch;  // run primitive tests when at least this many lanes are parked at a leaf
+    int fast_slab;   // 1: eligible rays use collide_fast
+    int _pad;
+};
 
 template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(128, 4) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                                  Counters* counters, WorkQueue* wq) {
+__global__ void __launch_bounds__(128, 6) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+                                                                  Counters* counters, WorkQueue* wq, Tuning tune) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const DNode* __restrict__ nodes = sc.nodes;
-    const uint32_t n_nodes = sc.n_nodes;
     const bool is_list = sc.root_kind != RTP_ROOT_BVH;
-    const uint32_t n_steps_end = is_list ? sc.n_prims : n_nodes;  // List roots walk the primitive run without slab gates
+    const uint32_t END = is_list ? sc.n_prims : sc.n_nodes;  // List roots walk the primitive run without slab gates
     LocalCounters lc = {0, 0, 0, 0};
 
+    // lane state: node == END && prim == kNoPrim  -> empty (no ray);  prim != kNoPrim -> parked at a leaf;  else walking
     D3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
     double tmin = 0.0;
     HitRec h;
     h.t = 0.0; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
-    uint32_t node = 0, prim = kNoPrim, kind = 0;
+    uint32_t node = END, prim = kNoPrim, kind = 0;
     size_t idx = 0;
-    int state = LANE_EMPTY;
+    bool fast = false, sx = false, sy = false, sz = false;
     bool more = true;  // warp-uniform: the queue may still hold rays
 
     for (;;) {
         // ---- refill -------------------------------------------------------------------------------
-        const unsigned empty = __ballot_sync(0xffffffffu, state == LANE_EMPTY);
-        if (empty == 0xffffffffu || (more && __popc(empty) >= kRefillMin)) {
-            if (more) {
-                const int cnt = __popc(empty), leader = __ffs(empty) - 1;
-                unsigned long long base = 0;
-                if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (state == LANE_EMPTY) {
-                    idx = static_cast<size_t>(base) + __popc(empty & lt_mask);
-                    if (idx < n) {
-                        const double2* rp = reinterpret_cast<const double2*>(rays + idx);
-                        const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-                        o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
-                        inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
-                        tmin = r3.x;
-                        h.t = r3.y; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
-                        node = 0;
-                        state = LANE_WALK;
-                        lc.rays++;
-                    }
+        const unsigned empty = __ballot_sync(0xffffffffu, node == END && prim == kNoPrim);
+        if (empty == 0xffffffffu || (more && __popc(empty) >= tune.refill_min)) {
+            if (!more) break;  // every lane is empty and the queue is drained
+            const int cnt = __popc(empty), leader = __ffs(empty) - 1;
+            unsigned long long base = 0;
+            if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
+            if (node == END && prim == kNoPrim) {
+                idx = static_cast<size_t>(base) + __popc(empty & lt_mask);
+                if (idx < n) {
+                    const double2* rp = reinterpret_cast<const double2*>(rays + idx);
+                    const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+                    o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
+                    inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
+                    tmin = r3.x;
+                    h.t = r3.y; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
+                    fast = tune.fast_slab && finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z) && finite(o.x) && finite(o.y) &&
+                           finite(o.z) && h.t >= tmin;
+                    sx = inv.x < 0.0; sy = inv.y < 0.0; sz = inv.z < 0.0;
+                    lc.rays++;
+                    node = 0;
+                    if (END == 0) write_hit<FULL>(sc, out, idx, o, d, h);  // empty List root: immediate miss
                 }
-                if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
             }
-            if (__ballot_sync(0xffffffffu, state != LANE_EMPTY) == 0u) {
-                if (!more) break;
-                continue;
-            }
+            if (__ballot_sync(0xffffffffu, node != END) == 0u) continue;
         }
 
-        // ---- walk: every walking lane visits one node per iteration -------------------------------
+        // ---- walk: every walking lane visits up to two nodes per vote -----------------------------
         for (;;) {
-            if (state == LANE_WALK) {
-                if (node >= n_steps_end) {
-                    write_hit<FULL>(sc, out, idx, o, d, h);
-                    state = LANE_EMPTY;
-                } else if (is_list) {
-                    prim = node; kind = __ldg(&nodes[node].kind);
-                    node = node + 1;
-                    state = LANE_PRIM;
-                } else {
-                    const double* nb = nodes[node].bmin;
-                    const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
-                    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
-                    if (COUNT) lc.node_visits++;
-                    if (collide_literal(b0, b1, b2, o, inv, tmin, h.t)) {
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                if (node != END && prim == kNoPrim) {
+                    if (is_list) {
+                        prim = node; kind = __ldg(&nodes[node].kind);
                         node = node + 1;
-                        if (meta.y != kNoPrim) { prim = meta.y; kind = meta.z; state = LANE_PRIM; }
                     } else {
-                        node = meta.x;
+                        const double* nb = nodes[node].bmin;
+                        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
+                        if (COUNT) lc.node_visits++;
+                        bool pass;
+                        if (fast) {
+                            const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
+                            pass = collide_fast(b0, b1, b2, o, inv, sx, sy, sz, tmin, h.t);
+                        } else {
+                            pass = collide_literal_slow(nodes + node, o.x, o.y, o.z, inv.x, inv.y, inv.z, tmin, h.t);
+                        }
+                        node = pass ? node + 1 : meta.x;
+                        if (pass && meta.y != kNoPrim) { prim = meta.y; kind = meta.z; }
                     }
+                    if (node == END && prim == kNoPrim) write_hit<FULL>(sc, out, idx, o, d, h);  // ray finished: lane is now empty
                 }
             }
-            const unsigned walking = __ballot_sync(0xffffffffu, state == LANE_WALK);
+            const unsigned walking = __ballot_sync(0xffffffffu, node != END && prim == kNoPrim);
             if (walking == 0u) break;
-            const unsigned parked = __ballot_sync(0xffffffffu, state == LANE_PRIM);
-            if (__popc(parked) >= kPrimBatch) break;
-            if (more && __popc(~(walking | parked)) >= kRefillMin) break;
+            const unsigned parked = __ballot_sync(0xffffffffu, prim != kNoPrim);
+            if (__popc(parked) >= tune.prim_batch) break;
+            if (more && __popc(~(walking | parked)) >= tune.refill_min) break;
         }
 
         // ---- primitive tests for the parked lanes ------------------------------------------------
-        if (state == LANE_PRIM) {
+        if (prim != kNoPrim) {
             const DPrim* p = sc.prims + prim;
             double t, u = 0.0, v = 0.0;
             bool hit;
@@ -435,8 +470,12 @@ __global__ void __launch_bounds__(128, 4) trace_persistent_kernel(DSceneView sc,
                 if (COUNT) lc.sphere_tests++;
                 hit = test_sphere(p, o, d, tmin, h.t, t);
             }
-            if (hit) { h.t = t; h.u = u; h.v = v; h.slot = prim; h.kind = kind; }
-            state = LANE_WALK;
+            if (hit) {  // bvh.rs:107-111: shrink t_max, later hit replaces
+                h.t = t; h.u = u; h.v = v; h.slot = prim; h.kind = kind;
+                if (!(t == t)) fast = false;  // a NaN t (possible only with non-finite geometry) sends the ray to the literal slab test
+            }
+            prim = kNoPrim;
+            if (node == END) write_hit<FULL>(sc, out, idx, o, d, h);  // that was the last leaf: ray finished
         }
     }
 
@@ -843,6 +882,7 @@ struct DeviceScene {
     unsigned queue_seq = 0;
     int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
+    Tuning tune{8, 8, 1, 0};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
@@ -918,6 +958,10 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         const char* env = std::getenv("RTP_TRACE_KERNEL");
         ds->use_simple_kernel = env && std::string(env) == "simple";
+        if (const char* v = std::getenv("RTP_REFILL_MIN")) ds->tune.refill_min = std::max(1, std::min(32, std::atoi(v)));
+        if (const char* v = std::getenv("RTP_PRIM_BATCH")) ds->tune.prim_batch = std::max(1, std::min(32, std::atoi(v)));
+        if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
+        if (!flat.boxes_finite) ds->tune.fast_slab = 0;
     }
     for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_begin);
@@ -965,11 +1009,11 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->persistent_blocks), want)));
         WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
         if (full) {
-            if (count) trace_persistent_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
-            else trace_persistent_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
+            if (count) trace_persistent_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
+            else trace_persistent_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
         } else {
-            if (count) trace_persistent_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
-            else trace_persistent_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq);
+            if (count) trace_persistent_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
+            else trace_persistent_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
         }
     }
     RTP_CUDA(cudaGetLastError());
@@ -1157,7 +1201,7 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
         if (rc == RTP_OK) rc = device_scene_upload(s->flat, &s->dev);
         if (rc != RTP_OK) { delete s; return rc; }
         s->n_leaves = static_cast<uint32_t>(s->flat.prims.size());
-        s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(s->flat.nodes.size()) : 0u;
+        s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? s->flat.n_reference_nodes : 0u;
         // the host copies of the big arrays are no longer needed
         std::vector<DNode>().swap(s->flat.nodes);
         std::vector<DPrim>().swap(s->flat.prims);
@@ -1195,7 +1239,7 @@ int rtp_bvh_build_order(const rtp_scene_desc* desc, uint32_t* leaf_ids_out, size
         }
         if (info) {
             info->n_leaves = static_cast<uint32_t>(flat.prims.size());
-            info->n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
+            info->n_nodes = flat.root_kind == RTP_ROOT_BVH ? flat.n_reference_nodes : 0u;
             info->depth = flat.depth; info->root_kind = flat.root_kind; info->device_bytes = 0;
         }
         return RTP_OK;

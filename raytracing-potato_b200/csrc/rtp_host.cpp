@@ -78,7 +78,7 @@ struct Builder {
         uint32_t left = base + 1, right = base + 1 + static_cast<uint32_t>(2 * nl - 1);
         int next_axis = (axis + 1) % 3;
         if (spawn_levels > 0 && n > 65536) {
-            auto fut = std::async(std::launch::async, [=] { build(lo, nl, left, next_axis, level + 1, spawn_levels - 1); });
+            auto fut = std::async(std::launch::async, [this, lo, nl, left, next_axis, level, spawn_levels] { build(lo, nl, left, next_axis, level + 1, spawn_levels - 1); });
             build(lo + nl, nr, right, next_axis, level + 1, spawn_levels - 1);
             fut.get();
         } else {
@@ -93,6 +93,93 @@ struct Builder {
         }
         nd.prim = kNoPrim;
         nd.kind = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device culling tree. The reference tree above fixes the ORDER in which leaves are met (its
+// depth-first rank) and nothing else: `Bvh::hit` is equivalent to scanning the leaves in rank
+// order, testing each leaf's own box and then its primitive against the running t_max, because an
+// ancestor box is a superset of the leaf box and IEEE rounding is monotone, so an ancestor test can
+// never reject a leaf whose own gate would pass. Any binary tree over the
+// rank-ordered leaf sequence therefore yields identical results, and we are free to choose the
+// split positions by surface-area heuristic instead of the median. (With the ground sphere of the
+// bunny scenes the median tree drags a 2000-unit box down 13 levels; the SAH tree isolates it.)
+// ---------------------------------------------------------------------------------------------
+struct SeqBuilder {
+    const std::vector<BuildItem>& items;  // in rank order
+    std::vector<DNode>& nodes;            // pre-order output, 2n-1 entries
+    std::atomic<uint32_t> depth{0};
+
+    struct Box {
+        double lo[3], hi[3];
+        void reset() { for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; } }
+        void grow(const double* bmin, const double* bmax) {
+            for (int k = 0; k < 3; ++k) { lo[k] = std::fmin(lo[k], bmin[k]); hi[k] = std::fmax(hi[k], bmax[k]); }
+        }
+        double half_area() const {
+            const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+            const double a = dx * dy + dy * dz + dz * dx;
+            return a == a ? a : std::numeric_limits<double>::infinity();
+        }
+    };
+
+    // split position k in [1, n-1] minimising area(L)*|L| + area(R)*|R|; ranges above kExact leaves are scanned at
+    // kChunks equally spaced candidates so the build stays O(n log n)
+    static constexpr size_t kExact = 4096, kChunks = 256;
+    size_t choose_split(size_t lo, size_t n) const {
+        const size_t step = n <= kExact ? 1 : (n + kChunks - 1) / kChunks;
+        const size_t m = (n + step - 1) / step;  // number of groups
+        std::vector<double> suffix(m + 1, 0.0);
+        Box b;
+        b.reset();
+        for (size_t g = m; g-- > 1;) {  // suffix[g] = area of groups g..m-1
+            for (size_t i = lo + g * step; i < std::min(lo + (g + 1) * step, lo + n); ++i) b.grow(items[i].bmin, items[i].bmax);
+            suffix[g] = b.half_area();
+        }
+        b.reset();
+        double best = std::numeric_limits<double>::infinity();
+        size_t best_k = n / 2;
+        for (size_t g = 0; g + 1 < m; ++g) {
+            for (size_t i = lo + g * step; i < lo + (g + 1) * step; ++i) b.grow(items[i].bmin, items[i].bmax);
+            const size_t k = (g + 1) * step;
+            const double cost = b.half_area() * static_cast<double>(k) + suffix[g + 1] * static_cast<double>(n - k);
+            if (cost < best) { best = cost; best_k = k; }
+        }
+        return best_k;
+    }
+
+    void build(size_t lo, size_t n, uint32_t base, uint32_t level, int spawn_levels) {
+        uint32_t seen = depth.load(std::memory_order_relaxed);
+        while (level > seen && !depth.compare_exchange_weak(seen, level, std::memory_order_relaxed)) {}
+        DNode& nd = nodes[base];
+        nd.skip = base + static_cast<uint32_t>(2 * n - 1);
+        nd._pad = 0;
+        nd.kind = 0;
+        if (n == 1) {
+            std::memcpy(nd.bmin, items[lo].bmin, sizeof nd.bmin);
+            std::memcpy(nd.bmax, items[lo].bmax, sizeof nd.bmax);
+            nd.prim = static_cast<uint32_t>(lo);
+            return;
+        }
+        // a pathological chain cannot exhaust the host stack: past 192 levels fall back to the median
+        const size_t nl = level < 192 ? choose_split(lo, n) : n / 2, nr = n - nl;
+        const uint32_t left = base + 1, right = base + 1 + static_cast<uint32_t>(2 * nl - 1);
+        if (spawn_levels > 0 && n > 65536) {
+            auto fut = std::async(std::launch::async, [this, lo, nl, left, level, spawn_levels] { build(lo, nl, left, level + 1, spawn_levels - 1); });
+            build(lo + nl, nr, right, level + 1, spawn_levels - 1);
+            fut.get();
+        } else {
+            build(lo, nl, left, level + 1, 0);
+            build(lo + nl, nr, right, level + 1, 0);
+        }
+        const DNode& l = nodes[left];
+        const DNode& r = nodes[right];
+        for (int k = 0; k < 3; ++k) {
+            nd.bmin[k] = min_num(l.bmin[k], r.bmin[k]);
+            nd.bmax[k] = max_num(l.bmax[k], r.bmax[k]);
+        }
+        nd.prim = kNoPrim;
     }
 };
 
@@ -195,9 +282,21 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
     if (d->root_kind == RTP_ROOT_BVH) {
         out->nodes.assign(static_cast<size_t>(2) * n - 1, DNode{});
         Builder b{items, out->nodes};
-        b.build(0, n, 0, 0, 1, 4);
+        b.build(0, n, 0, 0, 1, 4);  // sorts `items` into the reference's DFS-rank order
         out->depth = b.depth.load();
+        out->n_reference_nodes = static_cast<uint32_t>(out->nodes.size());
+        const char* tree = std::getenv("RTP_TREE");  // "reference" keeps the median-split topology on the device (A/B runs, counter parity)
+        if (!(tree && std::string(tree) == "reference")) {
+            SeqBuilder sb{items, out->nodes};
+            sb.build(0, n, 0, 1, 4);
+            out->device_depth = sb.depth.load();
+        } else {
+            out->device_depth = out->depth;
+        }
     }
+    for (const DNode& nd : out->nodes)
+        for (int k = 0; k < 3; ++k)
+            if (!std::isfinite(nd.bmin[k]) || !std::isfinite(nd.bmax[k])) out->boxes_finite = false;
     // List roots keep the caller's order (hittable.rs:113); Bvh roots are now in DFS-rank order.
 
     // ---- primitives in traversal order ----------------------------------------------------------

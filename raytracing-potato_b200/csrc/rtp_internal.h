@@ -99,7 +99,10 @@ struct FlatScene {
     std::vector<std::vector<uint8_t>> images;  // per texture (empty unless Image)
     std::vector<uint32_t> leaf_order;          // LeafId by DFS rank
     uint32_t root_kind = 0;
-    uint32_t depth = 0;
+    uint32_t depth = 0;              // of the reference tree (bvh.rs), what rtp_scene_info reports
+    uint32_t n_reference_nodes = 0;  // 2n-1
+    uint32_t device_depth = 0;       // of the culling tree the kernels walk
+    bool boxes_finite = true;  // every node box coordinate is finite (precondition of the sign-selected slab test)
     rtp_emit background{};
 };
 

@@ -92,16 +92,45 @@ def test_full_hit_record(bunny_pair):
     assert np.allclose(hg["uv"][sph], ho["uv"][sph], rtol=0, atol=1e-14)
 
 
-def test_counters_match_oracle(bunny_pair):
+def test_counters_match_oracle(bunny_pair, monkeypatch):
+    """Work counters. With the reference's own median-split topology on the device (RTP_TREE=reference) the kernel performs
+    exactly the oracle's AABB::collide evaluations; with the default SAH culling tree it visits fewer nodes but must run
+    exactly the same primitive tests (the same leaves get through their own slab gate, in the same order)."""
     sc, g, o = bunny_pair
     import torch
 
     rays = oracle.camera_rays(primary(sc, 640, 360), 640, 360)
     d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
     d_hits = torch.empty((len(rays), 2), dtype=torch.float64, device="cuda")
+    ho, so = o.hit_full(rays, stats=True)
     st = g.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
-    _, so = o.hit_full(rays, stats=True)
-    assert (st.rays, st.node_visits, st.triangle_tests, st.sphere_tests) == (so.rays, so.node_visits, so.triangle_tests, so.sphere_tests)
+    assert (st.rays, st.triangle_tests, st.sphere_tests) == (so.rays, so.triangle_tests, so.sphere_tests)
+    assert 0 < st.node_visits < so.node_visits
+    monkeypatch.setenv("RTP_TREE", "reference")
+    gr = api.Scene(sc)
+    monkeypatch.delenv("RTP_TREE")
+    sr = gr.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+    assert (sr.rays, sr.node_visits, sr.triangle_tests, sr.sphere_tests) == (so.rays, so.node_visits, so.triangle_tests, so.sphere_tests)
+    hits = d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1)
+    assert (hits["leaf"] == ho["leaf"]).all() and hits["t"].tobytes() == ho["t"].tobytes()
+    gr.close()
+
+
+@pytest.mark.parametrize("kernel,tree", [("simple", "reference"), ("simple", "sah"), ("persist", "reference")])
+def test_kernel_and_tree_variants_agree(gpu, monkeypatch, kernel, tree):
+    """every (kernel, culling tree) combination returns the oracle's hits: the baseline one-thread-per-ray kernel, the
+    persistent wavefront kernel, the reference topology and the SAH-over-rank-order topology"""
+    monkeypatch.setenv("RTP_TRACE_KERNEL", kernel)
+    monkeypatch.setenv("RTP_TREE", tree)
+    sc = scenes.bunny_lambert()
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    rays = np.concatenate([oracle.camera_rays(primary(sc, 480, 270), 480, 270), scenes.incoherent_rays(50000, seed=5), edge_rays().view(A.RAY_DTYPE).reshape(-1)])
+    assert_hits_equal_bits(g.hit(rays), o.hit(rays))
+    g.close(); o.close()
+
+
+def assert_hits_equal_bits(g, o):
+    assert (g["leaf"] == o["leaf"]).all() and (g["material"] == o["material"]).all() and g["t"].tobytes() == o["t"].tobytes()
 
 
 def edge_rays():
