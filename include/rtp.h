@@ -208,9 +208,11 @@ typedef struct rtp_render_params {
 typedef struct rtp_stats {
     uint64_t rays;          /* closest-hit queries (`scene.hit` calls, render.rs:105,133)  */
     uint64_t paths;         /* camera samples traced                                       */
-    uint64_t node_visits;   /* AABB::collide evaluations (RTP_RENDER_COUNTERS only)        */
+    uint64_t node_visits;   /* culling-tree nodes visited (counting kernels only)          */
     uint64_t triangle_tests;
     uint64_t sphere_tests;
+    uint64_t leaf_gates;    /* exact f64 AABB::collide evaluations at leaves (bvh.rs:96)   */
+    uint64_t conservative_violations; /* f32 culling decisions that contradicted the f64 test: must be 0 */
     double device_ms;       /* CUDA-event time of the device work of this call             */
     uint64_t kernel_launches;
 } rtp_stats;

@@ -133,6 +133,8 @@ class Stats(C.Structure):
         ("node_visits", C.c_uint64),
         ("triangle_tests", C.c_uint64),
         ("sphere_tests", C.c_uint64),
+        ("leaf_gates", C.c_uint64),
+        ("conservative_violations", C.c_uint64),
         ("device_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
     ]

@@ -59,11 +59,11 @@ __device__ __forceinline__ D3 normalize(D3 a) {
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 struct Counters {
-    unsigned long long rays, paths, node_visits, triangle_tests, sphere_tests;
+    unsigned long long rays, paths, node_visits, triangle_tests, sphere_tests, leaf_gates, violations;
 };
 
 struct LocalCounters {
-    unsigned int rays, node_visits, triangle_tests, sphere_tests;
+    unsigned int rays, node_visits, triangle_tests, sphere_tests, leaf_gates, violations;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -116,6 +116,34 @@ __device__ __noinline__ bool collide_literal_slow(const DNode* __restrict__ node
     const double* nb = node->bmin;
     return collide_literal(ldg2(nb), ldg2(nb + 2), ldg2(nb + 4), mk(ox, oy, oz), mk(ix, iy, iz), tmin, T);
 }
+
+// Conservative f32 culling. Inputs: the node's outward-inflated f32 box (rtp_internal.h DNode32), inv32 = RN32(1/d),
+// and per axis c_lo = RD32(-(o*inv) - K), c_hi = RU32(-(o*inv) + K) with K = 2^-21 |o*inv| + 1e-37. Then
+//   n_lo = fma(near_plane, inv32, c_lo) <= the f64 slab entry (min-o)*inv as the reference rounds it, and
+//   f_hi = fma(far_plane,  inv32, c_hi) >= the f64 slab exit,
+// for |o|, |box| <= 1e15 and 1e-15 <= |inv| <= 1e15 (no overflow/underflow trouble); the derivation is in DESIGN.md §4.
+// With T_up >= t_max and tmin_dn <= t_min, `min(T_up, f_hi) < max(tmin_dn, n_lo)` therefore implies that the reference's
+// f64 test `t_max >= t_min` is false for this box and for every box inside it: the subtree can be skipped. The converse
+// is not claimed: a node that is not rejected here is simply visited, and leaves get the exact f64 gate.
+struct Ray32 {
+    float ix, iy, iz;
+    float clx, cly, clz, chx, chy, chz;
+    float tmin_dn, T_up;
+};
+
+__device__ __forceinline__ bool collide32_reject(const float4 q0, const float2 q1, const Ray32& r, bool sx, bool sy, bool sz) {
+    // q0 = (min.x, min.y, min.z, max.x), q1 = (max.y, max.z)
+    const float pnx = sx ? q0.w : q0.x, pfx = sx ? q0.x : q0.w;
+    const float pny = sy ? q1.x : q0.y, pfy = sy ? q0.y : q1.x;
+    const float pnz = sz ? q1.y : q0.z, pfz = sz ? q0.z : q1.y;
+    const float nx = fmaf(pnx, r.ix, r.clx), ny = fmaf(pny, r.iy, r.cly), nz = fmaf(pnz, r.iz, r.clz);
+    const float fx = fmaf(pfx, r.ix, r.chx), fy = fmaf(pfy, r.iy, r.chy), fz = fmaf(pfz, r.iz, r.chz);
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, r.tmin_dn));
+    const float tf = fminf(fminf(fx, fy), fminf(fz, r.T_up));
+    return tf < tn;
+}
+
+__device__ __forceinline__ bool in_f32_range(double x) { const double a = fabs(x); return a >= 1e-15 && a <= 1e15; }
 
 __device__ __forceinline__ bool finite_nonzero(double x) { return x != 0.0 && fabs(x) <= 1.7976931348623157e308; }
 __device__ __forceinline__ bool finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
@@ -315,13 +343,15 @@ __device__ __forceinline__ void write_hit(const DSceneView& sc, void* __restrict
 template <bool COUNT>
 __device__ __forceinline__ void flush_counters(Counters* counters, const LocalCounters& lc) {
     if (!counters) return;
-    unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests;
+    unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests, lg = lc.leaf_gates, vi = lc.violations;
     for (int off = 16; off; off >>= 1) {
         r += __shfl_down_sync(0xffffffffu, r, off);
         if (COUNT) {
             nv += __shfl_down_sync(0xffffffffu, nv, off);
             tt += __shfl_down_sync(0xffffffffu, tt, off);
             st += __shfl_down_sync(0xffffffffu, st, off);
+            lg += __shfl_down_sync(0xffffffffu, lg, off);
+            vi += __shfl_down_sync(0xffffffffu, vi, off);
         }
     }
     if ((threadIdx.x & 31) == 0) {
@@ -330,6 +360,8 @@ __device__ __forceinline__ void flush_counters(Counters* counters, const LocalCo
             atomicAdd(&counters->node_visits, static_cast<unsigned long long>(nv));
             atomicAdd(&counters->triangle_tests, static_cast<unsigned long long>(tt));
             atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
+            atomicAdd(&counters->leaf_gates, static_cast<unsigned long long>(lg));
+            atomicAdd(&counters->violations, static_cast<unsigned long long>(vi));
         }
     }
 }
@@ -339,7 +371,7 @@ template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                             Counters* counters) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    LocalCounters lc = {0, 0, 0, 0};
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
     if (i < n) {
         const double2* rp = reinterpret_cast<const double2*>(rays + i);
         const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
@@ -373,110 +405,181 @@ struct Tuning {
     int refill_min;  // refill when at least this many lanes are empty
     int prim_batch;  // run primitive tests when at least this many lanes are parked at a leaf
     int fast_slab;   // 1: eligible rays use collide_fast
-    int _pad;
+    int f32_culling; // 1: eligible rays cull with the conservative f32 walk
 };
 
-template <bool COUNT, bool FULL>
-__global__ void __launch_bounds__(128, 6) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+// Per-lane traversal state shared by the ray-batch kernel and the path integrator.
+struct Walker {
+    D3 o, d, inv;
+    double tmin;
+    HitRec h;        // h.t is the running t_max
+    Ray32 r32;
+    uint32_t node;   // pre-order index, END when the walk is over
+    uint32_t prim;   // kNoPrim, or slot | kind << 31 of the leaf the lane is parked at
+    bool fast;       // eligible for collide_fast (finite, non-axis-parallel, no NaN)
+    bool m32;        // eligible for the f32 culling walk
+    bool need_gate;  // parked by the f32 walk: the leaf's exact f64 gate has not been evaluated yet
+    bool sx, sy, sz;
+};
+
+// utility.rs:71-77 Ray::expand plus the derived quantities of the fast paths
+__device__ __forceinline__ void walker_start(Walker& w, const DSceneView& sc, const Tuning& tune, D3 o, D3 d, double tmin, double tmax) {
+    w.o = o; w.d = d;
+    w.inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    w.tmin = tmin;
+    w.h.t = tmax; w.h.u = 0.0; w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
+    w.fast = tune.fast_slab && finite_nonzero(w.inv.x) && finite_nonzero(w.inv.y) && finite_nonzero(w.inv.z) && finite(o.x) && finite(o.y) &&
+             finite(o.z) && tmax >= tmin;
+    w.sx = w.inv.x < 0.0; w.sy = w.inv.y < 0.0; w.sz = w.inv.z < 0.0;
+    w.m32 = w.fast && tune.f32_culling && sc.f32_culling && in_f32_range(w.inv.x) && in_f32_range(w.inv.y) && in_f32_range(w.inv.z) &&
+            fabs(o.x) <= 1e15 && fabs(o.y) <= 1e15 && fabs(o.z) <= 1e15;
+    if (w.m32) {
+        const double px = o.x * w.inv.x, py = o.y * w.inv.y, pz = o.z * w.inv.z;
+        const double kx = fabs(px) * 0x1.0p-21 + 1e-37, ky = fabs(py) * 0x1.0p-21 + 1e-37, kz = fabs(pz) * 0x1.0p-21 + 1e-37;
+        w.r32.ix = __double2float_rn(w.inv.x); w.r32.iy = __double2float_rn(w.inv.y); w.r32.iz = __double2float_rn(w.inv.z);
+        w.r32.clx = __double2float_rd(-px - kx); w.r32.cly = __double2float_rd(-py - ky); w.r32.clz = __double2float_rd(-pz - kz);
+        w.r32.chx = __double2float_ru(-px + kx); w.r32.chy = __double2float_ru(-py + ky); w.r32.chz = __double2float_ru(-pz + kz);
+        w.r32.tmin_dn = __double2float_rd(tmin);
+        w.r32.T_up = __double2float_ru(tmax);
+    }
+    w.node = 0;
+    w.prim = kNoPrim;
+    w.need_gate = false;
+}
+
+// One culling step of an f32-eligible lane (node != END, not parked).
+template <bool COUNT>
+__device__ __forceinline__ void walker_step32(Walker& w, const DSceneView& sc, LocalCounters& lc) {
+    const float4* np = reinterpret_cast<const float4*>(sc.nodes32 + w.node);
+    const float4 q0 = __ldg(np);
+    const float4 q1 = __ldg(np + 1);
+    const bool reject = collide32_reject(q0, make_float2(q1.x, q1.y), w.r32, w.sx, w.sy, w.sz);
+    if (COUNT) {
+        lc.node_visits++;
+        if (reject) {  // the conservative test must never reject a box the exact test accepts
+            const double* nb = sc.nodes[w.node].bmin;
+            if (collide_literal(ldg2(nb), ldg2(nb + 2), ldg2(nb + 4), w.o, w.inv, w.tmin, w.h.t)) lc.violations++;
+        }
+    }
+    const uint32_t skip = __float_as_uint(q1.z), leaf = __float_as_uint(q1.w);
+    w.node = reject ? skip : w.node + 1;
+    if (!reject & (leaf != kNoPrim)) { w.prim = leaf; w.need_gate = true; }
+}
+
+// One exact f64 step for lanes outside the f32 path's preconditions (bvh.rs:93-119 literally, or collide_fast).
+template <bool COUNT>
+__device__ __forceinline__ void walker_step64(Walker& w, const DSceneView& sc, LocalCounters& lc) {
+    const double* nb = sc.nodes[w.node].bmin;
+    const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
+    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
+    if (COUNT) lc.node_visits++;
+    const bool pass = w.fast ? collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, w.h.t) : collide_literal(b0, b1, b2, w.o, w.inv, w.tmin, w.h.t);
+    w.node = pass ? w.node + 1 : meta.x;
+    if (pass & (meta.y != kNoPrim)) { w.prim = meta.y | (meta.z << 31); w.need_gate = false; }
+}
+
+// The parked lane's leaf: exact slab gate (bvh.rs:96) if still owed, then the primitive (bvh.rs:97), then un-park.
+template <bool COUNT>
+__device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, LocalCounters& lc) {
+    const uint32_t slot = w.prim & 0x7FFFFFFFu, kind = w.prim >> 31;
+    const DPrim* p = sc.prims + slot;
+    bool open = true;
+    if (w.need_gate) {
+        const double* pb = p->bmin;
+        if (COUNT) lc.leaf_gates++;
+        open = collide_fast(ldg2(pb), ldg2(pb + 2), ldg2(pb + 4), w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, w.h.t);
+    }
+    if (open) {
+        double t, u = 0.0, v = 0.0;
+        bool hit;
+        if (kind == RTP_HITTABLE_TRIANGLE) {
+            if (COUNT) lc.triangle_tests++;
+            hit = test_triangle(p, w.o, w.d, w.tmin, w.h.t, t, u, v);
+        } else {
+            if (COUNT) lc.sphere_tests++;
+            hit = test_sphere(p, w.o, w.d, w.tmin, w.h.t, t);
+        }
+        if (hit) {  // bvh.rs:107-111: shrink t_max, later hit replaces
+            w.h.t = t; w.h.u = u; w.h.v = v; w.h.slot = slot; w.h.kind = kind;
+            w.r32.T_up = __double2float_ru(t);
+            if (!(t == t)) { w.fast = false; w.m32 = false; }  // NaN t (non-finite geometry only): back to the literal test
+        }
+    }
+    w.prim = kNoPrim;
+}
+
+template <bool COUNT, bool FULL, bool LIST>
+__global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const DNode* __restrict__ nodes = sc.nodes;
-    const bool is_list = sc.root_kind != RTP_ROOT_BVH;
-    const uint32_t END = is_list ? sc.n_prims : sc.n_nodes;  // List roots walk the primitive run without slab gates
-    LocalCounters lc = {0, 0, 0, 0};
+    const uint32_t END = LIST ? sc.n_prims : sc.n_nodes;  // List roots walk the primitive run without slab gates
+    constexpr size_t kNoRay = ~static_cast<size_t>(0);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
 
-    // lane state: node == END && prim == kNoPrim  -> empty (no ray);  prim != kNoPrim -> parked at a leaf;  else walking
-    D3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
-    double tmin = 0.0;
-    HitRec h;
-    h.t = 0.0; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
-    uint32_t node = END, prim = kNoPrim, kind = 0;
-    size_t idx = 0;
-    bool fast = false, sx = false, sy = false, sz = false;
+    // lane state: node == END && prim == kNoPrim  -> empty (its finished ray, if any, is written at the next refill);
+    //             prim != kNoPrim                 -> parked at a leaf;  otherwise walking
+    Walker w;
+    w.o = w.d = w.inv = mk(0, 0, 0);
+    w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
+    w.node = END; w.prim = kNoPrim;
+    w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
+    w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    size_t idx = kNoRay;
     bool more = true;  // warp-uniform: the queue may still hold rays
 
     for (;;) {
-        // ---- refill -------------------------------------------------------------------------------
-        const unsigned empty = __ballot_sync(0xffffffffu, node == END && prim == kNoPrim);
+        // ---- retire finished rays and refill ----------------------------------------------------------
+        const bool is_empty = (w.node == END) & (w.prim == kNoPrim);
+        const unsigned empty = __ballot_sync(0xffffffffu, is_empty);
         if (empty == 0xffffffffu || (more && __popc(empty) >= tune.refill_min)) {
+            if (is_empty && idx != kNoRay) {
+                write_hit<FULL>(sc, out, idx, w.o, w.d, w.h);
+                idx = kNoRay;
+            }
             if (!more) break;  // every lane is empty and the queue is drained
             const int cnt = __popc(empty), leader = __ffs(empty) - 1;
             unsigned long long base = 0;
             if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
-            if (node == END && prim == kNoPrim) {
-                idx = static_cast<size_t>(base) + __popc(empty & lt_mask);
-                if (idx < n) {
-                    const double2* rp = reinterpret_cast<const double2*>(rays + idx);
+            if (is_empty) {
+                const size_t i = static_cast<size_t>(base) + __popc(empty & lt_mask);
+                if (i < n) {
+                    idx = i;
+                    const double2* rp = reinterpret_cast<const double2*>(rays + i);
                     const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-                    o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
-                    inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
-                    tmin = r3.x;
-                    h.t = r3.y; h.u = 0.0; h.v = 0.0; h.slot = kNoPrim; h.kind = 0;
-                    fast = tune.fast_slab && finite_nonzero(inv.x) && finite_nonzero(inv.y) && finite_nonzero(inv.z) && finite(o.x) && finite(o.y) &&
-                           finite(o.z) && h.t >= tmin;
-                    sx = inv.x < 0.0; sy = inv.y < 0.0; sz = inv.z < 0.0;
+                    walker_start(w, sc, tune, mk(r0.x, r0.y, r1.x), mk(r1.y, r2.x, r2.y), r3.x, r3.y);
+                    if (END == 0) w.node = END;
                     lc.rays++;
-                    node = 0;
-                    if (END == 0) write_hit<FULL>(sc, out, idx, o, d, h);  // empty List root: immediate miss
                 }
             }
-            if (__ballot_sync(0xffffffffu, node != END) == 0u) continue;
+            if (__ballot_sync(0xffffffffu, w.node != END) == 0u) continue;
         }
 
-        // ---- walk: every walking lane visits up to two nodes per vote -----------------------------
-        for (;;) {
+        if (LIST) {
+            // hittable.rs:110-120: every primitive, in caller order, no boxes
+            if (w.node != END) { w.prim = w.node | (__ldg(&sc.nodes[w.node].kind) << 31); w.need_gate = false; w.node = w.node + 1; }
+        } else {
+            // ---- hot walk: f32-eligible lanes visit up to two nodes per vote -------------------------------
+            for (;;) {
 #pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {
-                if (node != END && prim == kNoPrim) {
-                    if (is_list) {
-                        prim = node; kind = __ldg(&nodes[node].kind);
-                        node = node + 1;
-                    } else {
-                        const double* nb = nodes[node].bmin;
-                        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
-                        if (COUNT) lc.node_visits++;
-                        bool pass;
-                        if (fast) {
-                            const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
-                            pass = collide_fast(b0, b1, b2, o, inv, sx, sy, sz, tmin, h.t);
-                        } else {
-                            pass = collide_literal_slow(nodes + node, o.x, o.y, o.z, inv.x, inv.y, inv.z, tmin, h.t);
-                        }
-                        node = pass ? node + 1 : meta.x;
-                        if (pass && meta.y != kNoPrim) { prim = meta.y; kind = meta.z; }
-                    }
-                    if (node == END && prim == kNoPrim) write_hit<FULL>(sc, out, idx, o, d, h);  // ray finished: lane is now empty
-                }
+                for (int rep = 0; rep < 2; ++rep)
+                    if ((w.node != END) & (w.prim == kNoPrim) & w.m32) walker_step32<COUNT>(w, sc, lc);
+                const unsigned walking = __ballot_sync(0xffffffffu, (w.node != END) & (w.prim == kNoPrim) & w.m32);
+                if (walking == 0u) break;
+                const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
+                if (__popc(parked) >= tune.prim_batch) break;
+                if (more && __popc(~(walking | parked)) >= tune.refill_min) break;
             }
-            const unsigned walking = __ballot_sync(0xffffffffu, node != END && prim == kNoPrim);
-            if (walking == 0u) break;
-            const unsigned parked = __ballot_sync(0xffffffffu, prim != kNoPrim);
-            if (__popc(parked) >= tune.prim_batch) break;
-            if (more && __popc(~(walking | parked)) >= tune.refill_min) break;
+            // ---- lanes outside the f32 path's preconditions take one exact step per round ------------------
+            if (__any_sync(0xffffffffu, !w.m32)) {
+                if ((w.node != END) & (w.prim == kNoPrim) & !w.m32) walker_step64<COUNT>(w, sc, lc);
+            }
         }
 
-        // ---- primitive tests for the parked lanes ------------------------------------------------
-        if (prim != kNoPrim) {
-            const DPrim* p = sc.prims + prim;
-            double t, u = 0.0, v = 0.0;
-            bool hit;
-            if (kind == RTP_HITTABLE_TRIANGLE) {
-                if (COUNT) lc.triangle_tests++;
-                hit = test_triangle(p, o, d, tmin, h.t, t, u, v);
-            } else {
-                if (COUNT) lc.sphere_tests++;
-                hit = test_sphere(p, o, d, tmin, h.t, t);
-            }
-            if (hit) {  // bvh.rs:107-111: shrink t_max, later hit replaces
-                h.t = t; h.u = u; h.v = v; h.slot = prim; h.kind = kind;
-                if (!(t == t)) fast = false;  // a NaN t (possible only with non-finite geometry) sends the ray to the literal slab test
-            }
-            prim = kNoPrim;
-            if (node == END) write_hit<FULL>(sc, out, idx, o, d, h);  // that was the last leaf: ray finished
-        }
+        // ---- leaves: exact gate + primitive test for the parked lanes --------------------------------
+        if (w.prim != kNoPrim) walker_leaf<COUNT>(w, sc, lc);
     }
 
     flush_counters<COUNT>(counters, lc);
@@ -723,7 +826,7 @@ __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamer
     const size_t npix = static_cast<size_t>(rp.tile_w) * rp.tile_h;
     const size_t total = npix * rp.n_samples;
     const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    LocalCounters lc = {0, 0, 0, 0};
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
     if (p < total) {
         const uint32_t s_local = static_cast<uint32_t>(p / npix);
         const size_t pix = p % npix;
@@ -868,6 +971,7 @@ constexpr size_t kChunkRays = 1u << 18;  // 16 MiB of rays per pipeline stage
 struct DeviceScene {
     int device = 0;
     DNode* nodes = nullptr;
+    DNode32* nodes32 = nullptr;
     DPrim* prims = nullptr;
     DAttr* attrs = nullptr;
     DMaterial* materials = nullptr;
@@ -882,7 +986,7 @@ struct DeviceScene {
     unsigned queue_seq = 0;
     int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
-    Tuning tune{8, 8, 1, 0};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
+    Tuning tune{16, 8, 1, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
@@ -903,7 +1007,7 @@ static int upload(const std::vector<T>& v, T** out, uint64_t* bytes) {
 
 void device_scene_free(DeviceScene* ds) {
     if (!ds) return;
-    cudaFree(ds->nodes); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
+    cudaFree(ds->nodes); cudaFree(ds->nodes32); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
     for (uint8_t* p : ds->images) cudaFree(p);
     cudaFree(ds->counters);
     cudaFree(ds->queues);
@@ -933,6 +1037,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     ds->device = g_device;
     auto bail = [&](int code) { device_scene_free(ds); return code; };
     if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
+    if ((rc = upload(flat.nodes32, &ds->nodes32, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.materials, &ds->materials, &ds->bytes)) != RTP_OK) return bail(rc);
@@ -954,13 +1059,14 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, ds->device);
         int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, false>, 128, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, false, false>, 128, 0);
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         const char* env = std::getenv("RTP_TRACE_KERNEL");
         ds->use_simple_kernel = env && std::string(env) == "simple";
         if (const char* v = std::getenv("RTP_REFILL_MIN")) ds->tune.refill_min = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_PRIM_BATCH")) ds->tune.prim_batch = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
+        if (const char* v = std::getenv("RTP_F32_CULLING")) ds->tune.f32_culling = std::atoi(v) != 0;
         if (!flat.boxes_finite) ds->tune.fast_slab = 0;
     }
     for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
@@ -969,7 +1075,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     if (e != cudaSuccess) return bail(set_error(RTP_ERR_CUDA, std::string("scene resources: ") + cudaGetErrorString(e)));
 
     DSceneView& v = ds->view;
-    v.nodes = ds->nodes; v.prims = ds->prims; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
+    v.nodes = ds->nodes; v.nodes32 = ds->nodes32; v.prims = ds->prims;
+    v.f32_culling = (flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15) ? 1u : 0u; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
     v.n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
     v.n_prims = static_cast<uint32_t>(flat.prims.size());
     v.root_kind = flat.root_kind;
@@ -1008,13 +1115,16 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         const size_t want = (n + block - 1) / block;
         const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->persistent_blocks), want)));
         WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
-        if (full) {
-            if (count) trace_persistent_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
-            else trace_persistent_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
+        const bool list = ds->view.root_kind != RTP_ROOT_BVH;
+#define RTP_LAUNCH_PERSISTENT(C, F, L) trace_persistent_kernel<C, F, L><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune)
+        if (list) {
+            if (full) { if (count) RTP_LAUNCH_PERSISTENT(true, true, true); else RTP_LAUNCH_PERSISTENT(false, true, true); }
+            else { if (count) RTP_LAUNCH_PERSISTENT(true, false, true); else RTP_LAUNCH_PERSISTENT(false, false, true); }
         } else {
-            if (count) trace_persistent_kernel<true, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
-            else trace_persistent_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune);
+            if (full) { if (count) RTP_LAUNCH_PERSISTENT(true, true, false); else RTP_LAUNCH_PERSISTENT(false, true, false); }
+            else { if (count) RTP_LAUNCH_PERSISTENT(true, false, false); else RTP_LAUNCH_PERSISTENT(false, false, false); }
         }
+#undef RTP_LAUNCH_PERSISTENT
     }
     RTP_CUDA(cudaGetLastError());
     return RTP_OK;
@@ -1060,7 +1170,7 @@ static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hit
         float ms = 0.f;
         RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
         std::memset(stats, 0, sizeof *stats);
-        stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests;
+        stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations;
         stats->device_ms = ms; stats->kernel_launches = launches;
     }
     return RTP_OK;
@@ -1139,7 +1249,7 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
         RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
         std::memset(stats, 0, sizeof *stats);
         stats->rays = c.rays; stats->paths = static_cast<uint64_t>(npix) * ns_total;
-        stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests;
+        stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations;
         stats->device_ms = ms; stats->kernel_launches = launches;
     }
     return RTP_OK;
@@ -1204,6 +1314,7 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
         s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? s->flat.n_reference_nodes : 0u;
         // the host copies of the big arrays are no longer needed
         std::vector<DNode>().swap(s->flat.nodes);
+        std::vector<DNode32>().swap(s->flat.nodes32);
         std::vector<DPrim>().swap(s->flat.prims);
         std::vector<DAttr>().swap(s->flat.attrs);
         std::vector<std::vector<uint8_t>>().swap(s->flat.images);
@@ -1292,7 +1403,7 @@ int rtp_trace_closest_device_counted(rtp_scene* scene, const rtp_ray* d_rays, si
     float ms = 0.f;
     RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
     std::memset(stats, 0, sizeof *stats);
-    stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests;
+    stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations;
     stats->device_ms = ms; stats->kernel_launches = 1;
     return RTP_OK;
 }

@@ -295,8 +295,10 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
         }
     }
     for (const DNode& nd : out->nodes)
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 3; ++k) {
             if (!std::isfinite(nd.bmin[k]) || !std::isfinite(nd.bmax[k])) out->boxes_finite = false;
+            out->scene_mag = std::fmax(out->scene_mag, std::fmax(std::fabs(nd.bmin[k]), std::fabs(nd.bmax[k])));
+        }
     // List roots keep the caller's order (hittable.rs:113); Bvh roots are now in DFS-rank order.
 
     // ---- primitives in traversal order ----------------------------------------------------------
@@ -312,6 +314,8 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
         std::memset(&at, 0, sizeof at);
         p.leaf = id;
         out->leaf_order[slot] = id;
+        std::memcpy(p.bmin, items[slot].bmin, sizeof p.bmin);  // hittable.rs:124-140, the leaf's own gate box
+        std::memcpy(p.bmax, items[slot].bmax, sizeof p.bmax);
         if (h.kind == RTP_HITTABLE_SPHERE) {
             for (int k = 0; k < 3; ++k) p.a[k] = h.center[k];
             p.ba[0] = h.radius;
@@ -340,6 +344,22 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
     if (d->root_kind == RTP_ROOT_BVH) {
         for (DNode& nd : out->nodes)
             if (nd.prim != kNoPrim) nd.kind = d->hittables[items[nd.prim].id].kind;
+        // f32 culling copy: outward rounding + 2^-21 relative inflation (error budget in DESIGN.md §4)
+        out->nodes32.resize(out->nodes.size());
+        for (size_t k = 0; k < out->nodes.size(); ++k) {
+            const DNode& nd = out->nodes[k];
+            DNode32& q = out->nodes32[k];
+            for (int a = 0; a < 3; ++a) {
+                const double mag = std::fmax(std::fabs(nd.bmin[a]), std::fabs(nd.bmax[a]));
+                const double r = std::ldexp(mag, -21);
+                float lo = static_cast<float>(nd.bmin[a] - r), hi = static_cast<float>(nd.bmax[a] + r);
+                if (static_cast<double>(lo) > nd.bmin[a] - r) lo = std::nextafterf(lo, -std::numeric_limits<float>::infinity());
+                if (static_cast<double>(hi) < nd.bmax[a] + r) hi = std::nextafterf(hi, std::numeric_limits<float>::infinity());
+                q.bmin[a] = lo; q.bmax[a] = hi;
+            }
+            q.skip = nd.skip;
+            q.prim = nd.prim == kNoPrim ? kNoPrim : (nd.prim | (nd.kind << 31));
+        }
     } else {
         // a List root is traversed as a flat run of leaves without slab tests; nodes carry only the kind
         out->nodes.assign(n ? n : 1, DNode{});

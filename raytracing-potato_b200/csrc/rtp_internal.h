@@ -35,15 +35,30 @@ static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
 // One primitive per leaf (bvh.rs:43-47), stored in DFS-rank order so a traversal touches them
 // in increasing address order. Triangle: a, ba = a-b, ca = a-c precomputed on the host with the
 // same IEEE subtraction the reference performs per test (hittable.rs:71-72) — bit-identical.
-// Sphere: center in a[], radius in ba[0].
-struct alignas(16) DPrim {  // 80 B
+// Sphere: center in a[], radius in ba[0]. The leaf's own exact f64 box (the reference's per-leaf
+// slab gate, bvh.rs:96) travels with the primitive so gate + test need one 128-byte record.
+struct alignas(16) DPrim {  // 128 B
     double a[3];
     double ba[3];
     double ca[3];
     uint32_t leaf;      // LeafId handed back to the caller
     uint32_t material;  // MaterialId
+    double bmin[3];
+    double bmax[3];
 };
-static_assert(sizeof(DPrim) == 80, "DPrim must be 80 bytes");
+static_assert(sizeof(DPrim) == 128, "DPrim must be 128 bytes");
+
+// Culling node in f32: the node's f64 box rounded OUTWARD and inflated by 2^-21 * max(|min|,|max|)
+// per axis, so that an f32 slab evaluation with the matching ray-side slack is a rigorous lower /
+// upper bound of the f64 evaluation (rtp_device.cu, collide32_reject). Same pre-order
+// index space as DNode. prim: kNoPrim for branches, slot | kind << 31 for leaves.
+struct alignas(32) DNode32 {  // 32 B
+    float bmin[3];
+    float bmax[3];
+    uint32_t skip;
+    uint32_t prim;
+};
+static_assert(sizeof(DNode32) == 32, "DNode32 must be 32 bytes");
 
 // Shading attributes of a triangle (mesh.rs:7-11 normals/uvs of its three vertices), read once
 // per accepted path vertex, never during traversal.
@@ -74,6 +89,7 @@ struct DMaterial {
 
 struct DSceneView {  // passed by value to kernels
     const DNode* nodes;
+    const DNode32* nodes32;
     const DPrim* prims;
     const DAttr* attrs;
     const DMaterial* materials;
@@ -83,7 +99,7 @@ struct DSceneView {  // passed by value to kernels
     uint32_t root_kind;
     uint32_t bg_kind;
     uint32_t bg_texture;
-    uint32_t _pad;
+    uint32_t f32_culling;  // 1: scene magnitudes allow the f32 conservative slab test
     double bg_rgb[3];
 };
 
@@ -92,6 +108,7 @@ struct DSceneView {  // passed by value to kernels
 // ---------------------------------------------------------------------------------------------
 struct FlatScene {
     std::vector<DNode> nodes;
+    std::vector<DNode32> nodes32;
     std::vector<DPrim> prims;
     std::vector<DAttr> attrs;
     std::vector<DMaterial> materials;
@@ -102,6 +119,7 @@ struct FlatScene {
     uint32_t depth = 0;              // of the reference tree (bvh.rs), what rtp_scene_info reports
     uint32_t n_reference_nodes = 0;  // 2n-1
     uint32_t device_depth = 0;       // of the culling tree the kernels walk
+    double scene_mag = 0.0;    // largest |coordinate| of any node box
     bool boxes_finite = true;  // every node box coordinate is finite (precondition of the sign-selected slab test)
     rtp_emit background{};
 };

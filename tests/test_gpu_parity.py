@@ -106,9 +106,12 @@ def test_counters_match_oracle(bunny_pair, monkeypatch):
     st = g.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
     assert (st.rays, st.triangle_tests, st.sphere_tests) == (so.rays, so.triangle_tests, so.sphere_tests)
     assert 0 < st.node_visits < so.node_visits
+    assert st.conservative_violations == 0  # the f32 culling test never rejected a box the exact f64 test accepts
     monkeypatch.setenv("RTP_TREE", "reference")
+    monkeypatch.setenv("RTP_F32_CULLING", "0")  # exact f64 slab tests only: the node-visit count must equal the oracle's
     gr = api.Scene(sc)
     monkeypatch.delenv("RTP_TREE")
+    monkeypatch.delenv("RTP_F32_CULLING")
     sr = gr.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
     assert (sr.rays, sr.node_visits, sr.triangle_tests, sr.sphere_tests) == (so.rays, so.node_visits, so.triangle_tests, so.sphere_tests)
     hits = d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1)
@@ -116,12 +119,14 @@ def test_counters_match_oracle(bunny_pair, monkeypatch):
     gr.close()
 
 
-@pytest.mark.parametrize("kernel,tree", [("simple", "reference"), ("simple", "sah"), ("persist", "reference")])
-def test_kernel_and_tree_variants_agree(gpu, monkeypatch, kernel, tree):
+@pytest.mark.parametrize("kernel,tree,f32", [("simple", "reference", 1), ("simple", "sah", 1), ("persist", "reference", 1), ("persist", "sah", 0),
+                                             ("persist", "reference", 0)])
+def test_kernel_and_tree_variants_agree(gpu, monkeypatch, kernel, tree, f32):
     """every (kernel, culling tree) combination returns the oracle's hits: the baseline one-thread-per-ray kernel, the
     persistent wavefront kernel, the reference topology and the SAH-over-rank-order topology"""
     monkeypatch.setenv("RTP_TRACE_KERNEL", kernel)
     monkeypatch.setenv("RTP_TREE", tree)
+    monkeypatch.setenv("RTP_F32_CULLING", str(f32))
     sc = scenes.bunny_lambert()
     g, o = api.Scene(sc), oracle.Scene(sc)
     rays = np.concatenate([oracle.camera_rays(primary(sc, 480, 270), 480, 270), scenes.incoherent_rays(50000, seed=5), edge_rays().view(A.RAY_DTYPE).reshape(-1)])
