@@ -305,9 +305,19 @@ __device__ __forceinline__ void finish_sphere(const DSceneView& sc, const HitRec
 // kernels: ray batches
 // ---------------------------------------------------------------------------------------------
 
-template <bool FULL>
+// Output record of the traversal kernel inside the wavefront integrator: what shading needs to rebuild the
+// reference's `Hit` (t, barycentrics, primitive slot | kind << 31; slot == kNoPrim on a miss). 32 bytes.
+struct alignas(16) WaveHit {
+    double t, u, v;
+    uint32_t slotkind, _pad;
+};
+static_assert(sizeof(WaveHit) == 32, "WaveHit must be 32 bytes");
+
+enum { OUT_HIT = 0, OUT_FULL = 1, OUT_WAVE = 2 };
+
+template <int OUT>
 __device__ __forceinline__ void write_hit(const DSceneView& sc, void* __restrict__ out, size_t i, D3 o, D3 d, const HitRec& h) {
-    if (FULL) {
+    if (OUT == OUT_FULL) {
         rtp_hit_full* o_full = static_cast<rtp_hit_full*>(out) + i;
         rtp_hit_full r;
         if (h.slot != kNoPrim) {
@@ -324,6 +334,10 @@ __device__ __forceinline__ void write_hit(const DSceneView& sc, void* __restrict
             r.leaf = RTP_MISS; r.material = RTP_MISS; r.t = CUDART_INF;
         }
         *o_full = r;
+    } else if (OUT == OUT_WAVE) {
+        double2* w = reinterpret_cast<double2*>(static_cast<WaveHit*>(out) + i);
+        w[0] = make_double2(h.t, h.u);
+        w[1] = make_double2(h.v, __hiloint2double(0, static_cast<int>(h.slot == kNoPrim ? kNoPrim : (h.slot | (h.kind << 31)))));
     } else {
         uint4 w;
         if (h.slot != kNoPrim) {
@@ -379,7 +393,7 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const
         HitRec h;
         h.t = r3.y; h.u = 0.0; h.v = 0.0; h.kind = 0;
         closest_hit<COUNT>(sc, o, d, r3.x, h, lc);
-        write_hit<FULL>(sc, out, i, o, d, h);
+        write_hit<FULL ? OUT_FULL : OUT_HIT>(sc, out, i, o, d, h);
     }
     flush_counters<COUNT>(counters, lc);
 }
@@ -508,9 +522,10 @@ __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, Loc
     w.prim = kNoPrim;
 }
 
-template <bool COUNT, bool FULL, bool LIST>
+template <bool COUNT, int OUT, bool LIST>
 __global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                                  Counters* counters, WorkQueue* wq, Tuning tune) {
+                                                                  Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev) {
+    if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t END = LIST ? sc.n_prims : sc.n_nodes;  // List roots walk the primitive run without slab gates
@@ -534,7 +549,7 @@ __global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc,
         const unsigned empty = __ballot_sync(0xffffffffu, is_empty);
         if (empty == 0xffffffffu || (more && __popc(empty) >= tune.refill_min)) {
             if (is_empty && idx != kNoRay) {
-                write_hit<FULL>(sc, out, idx, w.o, w.d, w.h);
+                write_hit<OUT>(sc, out, idx, w.o, w.d, w.h);
                 idx = kNoRay;
             }
             if (!more) break;  // every lane is empty and the queue is drained
@@ -806,9 +821,14 @@ __device__ __forceinline__ D3 emit_evaluate(const DSceneView& sc, uint32_t kind,
 __device__ __forceinline__ D3 reflect(D3 incident, D3 normal) { return incident - (2.0 * dot(incident, normal)) * normal; }
 
 // ---------------------------------------------------------------------------------------------
-// K2-K6: one thread per camera path (main.rs:70-83 + render.rs:94-146). Per-sample colours go to a
-// scratch buffer and are summed in sample order by resolve_kernel, which reproduces the
-// reference's sequential `final_color += …` (main.rs:80) bit for bit.
+// K2-K6: the per-pixel bounce loop (main.rs:70-83 + render.rs:94-146).
+//
+// One path vertex is shaded by shade_vertex(): it rebuilds the reference's `Hit` for the winner,
+// runs Material::evaluate (scatter -> absorb -> emit, material.rs:104-110) and either ends the path
+// or produces the scattered ray. Radiance is folded inside-out like the recursion (render.rs:108-115):
+// (emit, absorb) of every scattering vertex go on a per-path stack and are combined when the path ends.
+// Per-sample colours go to a scratch buffer and are summed in sample order by resolve_kernel, which
+// reproduces the reference's sequential `final_color += ...` (main.rs:80) bit for bit.
 // ---------------------------------------------------------------------------------------------
 
 struct DRender {
@@ -820,6 +840,88 @@ struct DRender {
     unsigned long long seed;
 };
 
+// path p of a launch = (tile pixel p / n_samples, sample p % n_samples): the samples of one pixel sit in adjacent lanes,
+// so a warp's primary rays are as coherent as they can be
+__device__ __forceinline__ void path_coords(const DRender& rp, size_t p, uint32_t& i, uint32_t& j, uint32_t& smp) {
+    const size_t pix = p / rp.n_samples;
+    smp = rp.sample_begin + static_cast<uint32_t>(p % rp.n_samples);
+    i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
+    j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+}
+
+// main.rs:70-76: jittered uv (render.rs:76-81), lens sample (render.rs:36, drawn even when lens_radius == 0), Camera::shoot
+__device__ __forceinline__ void primary_ray(const DCamera& cam, const DRender& rp, uint32_t i, uint32_t j, Rng& rng, D3& o, D3& d) {
+    const double u = (static_cast<double>(i) + rng_next(rng)) / static_cast<double>(rp.width);
+    const double v = (static_cast<double>(j) + rng_next(rng)) / static_cast<double>(rp.height);
+    double lx, ly;
+    sample_unit_disk(rng, lx, ly);
+    camera_shoot(cam, u, v, cam.lens_radius * lx, cam.lens_radius * ly, o, d);
+}
+
+// render.rs:118,144 + utility.rs:93-100 Hit::at_infinity + background.evaluate
+__device__ __forceinline__ D3 shade_miss(const DSceneView& sc, D3 d) {
+    const double hu = 0.5 - atan2(d.z, d.x) / kTau, hv = asin(d.y) / kPi + 0.5;
+    return emit_evaluate(sc, sc.bg_kind, sc.bg_texture, sc.bg_rgb, d, d, d, hu, hv);
+}
+
+// render.rs:105-115 for a hit: returns true when the material scattered (then o, d hold the scattered ray, render.rs:111-114).
+__device__ __forceinline__ bool shade_vertex(const DSceneView& sc, D3& o, D3& d, const HitRec& h, Rng& rng, D3& emit, D3& absorb) {
+    Surface s;
+    finish_hit(sc, o, d, h, s);
+    if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
+    else finish_sphere(sc, h, s);
+    const DMaterial* m = sc.materials + s.material;
+
+    // material.rs:104-110: scatter, then absorb, then emit
+    bool scattered = false;
+    D3 sd = mk(0.0, 0.0, 0.0);
+    const uint32_t scatter = __ldg(&m->scatter);
+    if (scatter == RTP_SCATTER_LAMBERT) {  // material.rs:115-130
+        if (!(dot(s.normal, d) > 0.0)) {
+            sd = normalize(s.normal + sample_unit_sphere(rng));
+            scattered = true;
+        }
+    } else if (scatter == RTP_SCATTER_METAL) {  // material.rs:132-152
+        if (!(dot(s.normal, d) > 0.0)) {
+            const D3 refl = reflect(d, s.normal);
+            const D3 fz = __ldg(&m->scatter_param) * sample_unit_ball(rng);
+            sd = normalize(refl + fz);
+            scattered = !(dot(s.normal, sd) < 0.0);
+        }
+    } else if (scatter == RTP_SCATTER_DIELECTRIC) {  // material.rs:154-180
+        const double ior = __ldg(&m->scatter_param);
+        double eta;
+        D3 n;
+        if (dot(s.normal, d) > 0.0) { eta = ior; n = mk(-s.normal.x, -s.normal.y, -s.normal.z); }
+        else { eta = 1.0 / ior; n = s.normal; }
+        const double q = (1.0 - eta) / (1.0 + eta);
+        const double r0 = q * q;  // powi(2)
+        const double x = 1.0 + dot(n, d);
+        const double x2 = x * x;
+        const double reflectance = r0 + (1.0 - r0) * (x * (x2 * x2));  // powi(5)
+        if (rng_next(rng) < reflectance) {
+            sd = reflect(d, n);
+        } else {  // utility.rs:110-119 refract, else reflect
+            const double cos_theta = dot(n, d);
+            const double k = 1.0 - eta * eta * (1.0 - cos_theta * cos_theta);
+            if (k < 0.0) sd = reflect(d, n);
+            else sd = eta * d - (eta * cos_theta + sqrt(k)) * n;
+        }
+        scattered = true;
+    }
+    switch (__ldg(&m->absorb)) {  // material.rs:74-81
+        case RTP_ABSORB_WHITEBODY: absorb = mk(1.0, 1.0, 1.0); break;
+        case RTP_ABSORB_ALBEDO: absorb = mk(__ldg(&m->absorb_rgb[0]), __ldg(&m->absorb_rgb[1]), __ldg(&m->absorb_rgb[2])); break;
+        case RTP_ABSORB_ALBEDO_MAP: absorb = texture_sample(sc, __ldg(&m->absorb_texture), s.position, s.u, s.v); break;
+        default: absorb = mk(0.0, 0.0, 0.0); break;
+    }
+    emit = emit_evaluate(sc, __ldg(&m->emit_kind), __ldg(&m->emit_texture), m->emit_rgb, d, s.position, s.normal, s.u, s.v);
+    o = s.position; d = sd;
+    return scattered;
+}
+
+// Baseline integrator: one thread per camera path, whole bounce loop in one thread, exact f64 stack-free walk.
+// Kept for A/B runs (RTP_RENDER_KERNEL=simple) and as the second implementation the wavefront path is tested against.
 template <int MAXB, bool COUNT>
 __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamera cam, DRender rp, double4* __restrict__ scratch,
                                                             Counters* counters) {
@@ -828,21 +930,12 @@ __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamer
     const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     LocalCounters lc = {0, 0, 0, 0, 0, 0};
     if (p < total) {
-        const uint32_t s_local = static_cast<uint32_t>(p / npix);
-        const size_t pix = p % npix;
-        const uint32_t i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
-        const uint32_t j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
-        const uint32_t smp = rp.sample_begin + s_local;
-
+        uint32_t i, j, smp;
+        path_coords(rp, p, i, j, smp);
         Rng rng;
         rng_init(rng, rp.seed, j * rp.width + i, smp, RTP_RNG_STREAM_PATH);
-        // render.rs:76-81 make_uv_jitter
-        const double u = (static_cast<double>(i) + rng_next(rng)) / static_cast<double>(rp.width);
-        const double v = (static_cast<double>(j) + rng_next(rng)) / static_cast<double>(rp.height);
-        double lx, ly;
-        sample_unit_disk(rng, lx, ly);  // drawn even when lens_radius == 0 (render.rs:36)
         D3 o, d;
-        camera_shoot(cam, u, v, cam.lens_radius * lx, cam.lens_radius * ly, o, d);
+        primary_ray(cam, rp, i, j, rng, o, d);
 
         double emit_stack[MAXB][3], absorb_stack[MAXB][3];
         int nb = 0;
@@ -854,72 +947,16 @@ __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamer
             HitRec h;
             h.t = CUDART_INF; h.u = 0.0; h.v = 0.0; h.kind = 0;
             closest_hit<COUNT>(sc, o, d, kRayEpsilon, h, lc);
-            if (h.slot == kNoPrim) {
-                // render.rs:118,144 + utility.rs:93-100 Hit::at_infinity
-                const double hu = 0.5 - atan2(d.z, d.x) / kTau, hv = asin(d.y) / kPi + 0.5;
-                L = emit_evaluate(sc, sc.bg_kind, sc.bg_texture, sc.bg_rgb, d, d, d, hu, hv);
-                break;
-            }
+            if (h.slot == kNoPrim) { L = shade_miss(sc, d); break; }
             if (first) first_hit = true;
-            Surface s;
-            finish_hit(sc, o, d, h, s);
-            if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
-            else finish_sphere(sc, h, s);
-            const DMaterial* m = sc.materials + s.material;
-
-            // material.rs:104-110: scatter, then absorb, then emit
-            bool scattered = false;
-            D3 sd = mk(0.0, 0.0, 0.0);
-            const uint32_t scatter = __ldg(&m->scatter);
-            if (scatter == RTP_SCATTER_LAMBERT) {  // material.rs:115-130
-                if (!(dot(s.normal, d) > 0.0)) {
-                    sd = normalize(s.normal + sample_unit_sphere(rng));
-                    scattered = true;
-                }
-            } else if (scatter == RTP_SCATTER_METAL) {  // material.rs:132-152
-                if (!(dot(s.normal, d) > 0.0)) {
-                    const D3 refl = reflect(d, s.normal);
-                    const D3 fz = __ldg(&m->scatter_param) * sample_unit_ball(rng);
-                    sd = normalize(refl + fz);
-                    scattered = !(dot(s.normal, sd) < 0.0);
-                }
-            } else if (scatter == RTP_SCATTER_DIELECTRIC) {  // material.rs:154-180
-                const double ior = __ldg(&m->scatter_param);
-                double eta;
-                D3 n;
-                if (dot(s.normal, d) > 0.0) { eta = ior; n = mk(-s.normal.x, -s.normal.y, -s.normal.z); }
-                else { eta = 1.0 / ior; n = s.normal; }
-                const double q = (1.0 - eta) / (1.0 + eta);
-                const double r0 = q * q;  // powi(2)
-                const double x = 1.0 + dot(n, d);
-                const double x2 = x * x;
-                const double reflectance = r0 + (1.0 - r0) * (x * (x2 * x2));  // powi(5)
-                if (rng_next(rng) < reflectance) {
-                    sd = reflect(d, n);
-                } else {  // utility.rs:110-119 refract, else reflect
-                    const double cos_theta = dot(n, d);
-                    const double k = 1.0 - eta * eta * (1.0 - cos_theta * cos_theta);
-                    if (k < 0.0) sd = reflect(d, n);
-                    else sd = eta * d - (eta * cos_theta + sqrt(k)) * n;
-                }
-                scattered = true;
-            }
-            D3 absorb;
-            switch (__ldg(&m->absorb)) {  // material.rs:74-81
-                case RTP_ABSORB_WHITEBODY: absorb = mk(1.0, 1.0, 1.0); break;
-                case RTP_ABSORB_ALBEDO: absorb = mk(__ldg(&m->absorb_rgb[0]), __ldg(&m->absorb_rgb[1]), __ldg(&m->absorb_rgb[2])); break;
-                case RTP_ABSORB_ALBEDO_MAP: absorb = texture_sample(sc, __ldg(&m->absorb_texture), s.position, s.u, s.v); break;
-                default: absorb = mk(0.0, 0.0, 0.0); break;
-            }
-            const D3 emit = emit_evaluate(sc, __ldg(&m->emit_kind), __ldg(&m->emit_texture), m->emit_rgb, d, s.position, s.normal, s.u, s.v);
-            if (!scattered) {  // render.rs:108-110: emit + rgb(0,0,0)
+            D3 emit, absorb;
+            if (!shade_vertex(sc, o, d, h, rng, emit, absorb)) {  // render.rs:108-110: emit + rgb(0,0,0)
                 L = emit + mk(0.0, 0.0, 0.0);
                 break;
             }
             emit_stack[nb][0] = emit.x; emit_stack[nb][1] = emit.y; emit_stack[nb][2] = emit.z;
             absorb_stack[nb][0] = absorb.x; absorb_stack[nb][1] = absorb.y; absorb_stack[nb][2] = absorb.z;
             ++nb;
-            o = s.position; d = sd;
             depth -= 1;
             first = false;
         }
@@ -932,6 +969,122 @@ __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamer
     flush_counters<COUNT>(counters, lc);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wavefront integrator. A launch of P paths runs as
+//     generate -> [ trace_persistent_kernel (OUT_WAVE) -> shade ] x max_bounce
+// over ray queues in HBM. Queue b holds the rays of segment b of every path that is still alive, densely packed
+// (shade compacts survivors with one atomic per warp), so the traversal kernel always sees full warps. Queue
+// sizes live on the device (WaveQueues::count[b]); nothing synchronises with the host until the frame is done.
+// Per queue entry: ray (64 B), path state (16 B); per path: one (emit, absorb) pair per scattering vertex (48 B)
+// in a [bounce][path] stack, read back once when the path ends.
+// ---------------------------------------------------------------------------------------------
+
+struct WaveQueues {
+    rtp_ray* rays[2];
+    uint4* state[2];             // x = path index, y = next RNG draw, z = depth_left | nb << 8 | first_hit << 16
+    WaveHit* hits;
+    double2* stack;              // [bounce][path][3] double2: (emit.x, emit.y) (emit.z, absorb.x) (absorb.y, absorb.z)
+    unsigned long long* count;   // [max_bounce + 1]
+    size_t capacity;             // paths per launch the buffers were sized for (stride of `stack`)
+};
+
+__global__ void __launch_bounds__(256) wave_generate_kernel(DCamera cam, DRender rp, WaveQueues wq, size_t total) {
+    const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p == 0) wq.count[0] = total;
+    if (p >= total) return;
+    uint32_t i, j, smp;
+    path_coords(rp, p, i, j, smp);
+    Rng rng;
+    rng_init(rng, rp.seed, j * rp.width + i, smp, RTP_RNG_STREAM_PATH);
+    D3 o, d;
+    primary_ray(cam, rp, i, j, rng, o, d);
+    double2* out = reinterpret_cast<double2*>(wq.rays[0] + p);
+    out[0] = make_double2(o.x, o.y);
+    out[1] = make_double2(o.z, d.x);
+    out[2] = make_double2(d.y, d.z);
+    out[3] = make_double2(kRayEpsilon, CUDART_INF);
+    wq.state[0][p] = make_uint4(static_cast<uint32_t>(p), rng.k, rp.max_bounce, 0u);
+}
+
+__global__ void __launch_bounds__(256) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch) {
+    const size_t n = static_cast<size_t>(wq.count[bounce]);
+    const int cur = bounce & 1, nxt = cur ^ 1;
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    // warp-uniform trip count: every lane of a warp takes part in the compaction ballot
+    for (size_t q0 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) - lane; q0 < n; q0 += stride) {
+        const size_t q = q0 + lane;
+        bool alive = false;
+        D3 o = mk(0, 0, 0), d = mk(0, 0, 0);
+        uint4 st = make_uint4(0, 0, 0, 0);
+        if (q < n) {
+            const double2* rp2 = reinterpret_cast<const double2*>(wq.rays[cur] + q);
+            const double2 r0 = rp2[0], r1 = rp2[1], r2 = rp2[2];
+            o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
+            st = wq.state[cur][q];
+            const double2* hp = reinterpret_cast<const double2*>(wq.hits + q);
+            const double2 h0 = hp[0], h1 = hp[1];
+            const uint32_t slotkind = static_cast<uint32_t>(__double2loint(h1.y));
+            uint32_t depth = st.z & 0xFFu, nb = (st.z >> 8) & 0xFFu, first_hit = (st.z >> 16) & 1u;
+            const size_t p = st.x;
+            D3 L = mk(0.0, 0.0, 0.0);
+            if (slotkind == kNoPrim) {
+                L = shade_miss(sc, d);
+            } else {
+                if (bounce == 0) first_hit = 1u;
+                HitRec h;
+                h.t = h0.x; h.u = h0.y; h.v = h1.x; h.slot = slotkind & 0x7FFFFFFFu; h.kind = slotkind >> 31;
+                uint32_t i, j, smp;
+                path_coords(rp, p, i, j, smp);
+                Rng rng;
+                rng_init(rng, rp.seed, j * rp.width + i, smp, RTP_RNG_STREAM_PATH);
+                rng.k = st.y;
+                D3 emit, absorb;
+                if (!shade_vertex(sc, o, d, h, rng, emit, absorb)) {  // render.rs:108-110: emit + rgb(0,0,0)
+                    L = emit + mk(0.0, 0.0, 0.0);
+                } else {
+                    double2* sp = wq.stack + (static_cast<size_t>(nb) * wq.capacity + p) * 3;
+                    sp[0] = make_double2(emit.x, emit.y);
+                    sp[1] = make_double2(emit.z, absorb.x);
+                    sp[2] = make_double2(absorb.y, absorb.z);
+                    ++nb;
+                    depth -= 1;
+                    st.y = rng.k;
+                    if (depth == 0) L = mk(0.0, 0.0, 0.0);  // render.rs:128-131: the continuation returns black without tracing
+                    else alive = true;
+                }
+            }
+            if (!alive) {
+                // render.rs:108-115 / 135-142: emit + absorb ⊙ (inner), folded inside-out like the recursion
+                for (int b = static_cast<int>(nb) - 1; b >= 0; --b) {
+                    const double2* sp = wq.stack + (static_cast<size_t>(b) * wq.capacity + p) * 3;
+                    const double2 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+                    L = mk(s0.x, s0.y, s1.x) + cmul(mk(s1.y, s2.x, s2.y), L);
+                }
+                scratch[p] = make_double4(L.x, L.y, L.z, first_hit ? 1.0 : 0.0);
+            }
+            st.z = depth | (nb << 8) | (first_hit << 16);
+        }
+        // compaction: survivors of this warp take consecutive slots of the next queue
+        const unsigned live = __ballot_sync(0xffffffffu, alive);
+        if (live) {
+            const int leader = __ffs(live) - 1;
+            unsigned long long base = 0;
+            if (static_cast<int>(lane) == leader) base = atomicAdd(&wq.count[bounce + 1], static_cast<unsigned long long>(__popc(live)));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (alive) {
+                const size_t dst = static_cast<size_t>(base) + __popc(live & ((1u << lane) - 1u));
+                double2* out = reinterpret_cast<double2*>(wq.rays[nxt] + dst);
+                out[0] = make_double2(o.x, o.y);
+                out[1] = make_double2(o.z, d.x);
+                out[2] = make_double2(d.y, d.z);
+                out[3] = make_double2(kRayEpsilon, CUDART_INF);
+                wq.state[nxt][dst] = st;
+            }
+        }
+    }
+}
+
 // main.rs:78-87: per pixel, add the samples of this launch in sample order to the running sums; on the
 // last launch optionally divide by num_samples. acc is (r,g,b,foreground) per tile pixel.
 __global__ void __launch_bounds__(256) resolve_kernel(const double4* __restrict__ scratch, double4* __restrict__ acc, size_t npix, uint32_t n_samples,
@@ -940,7 +1093,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const double4* __restrict_
     if (pix >= npix) return;
     double4 a = first_launch ? make_double4(0.0, 0.0, 0.0, 0.0) : acc[pix];
     for (uint32_t s = 0; s < n_samples; ++s) {
-        const double4 c = scratch[static_cast<size_t>(s) * npix + pix];
+        const double4 c = scratch[pix * n_samples + s];  // path_coords: the samples of a pixel are adjacent
         a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
     }
     acc[pix] = a;
@@ -993,6 +1146,10 @@ struct DeviceScene {
     void* stage_hits[kPipeDepth] = {nullptr, nullptr, nullptr};
     double4* scratch = nullptr; size_t scratch_elems = 0;
     double4* acc = nullptr; size_t acc_elems = 0;
+    WaveQueues wave{};                 // wavefront integrator queues (render_device), grown on demand
+    uint32_t wave_bounces = 0;         // stack depth the queues were sized for
+    int shade_blocks = 0;              // grid of wave_shade_kernel
+    bool use_simple_render = false;    // RTP_RENDER_KERNEL=simple
     double* frame = nullptr; size_t frame_elems = 0;
 };
 
@@ -1018,6 +1175,8 @@ void device_scene_free(DeviceScene* ds) {
     if (ds->ev_begin) cudaEventDestroy(ds->ev_begin);
     if (ds->ev_end) cudaEventDestroy(ds->ev_end);
     cudaFree(ds->scratch); cudaFree(ds->acc); cudaFree(ds->frame);
+    cudaFree(ds->wave.rays[0]); cudaFree(ds->wave.rays[1]); cudaFree(ds->wave.state[0]); cudaFree(ds->wave.state[1]);
+    cudaFree(ds->wave.hits); cudaFree(ds->wave.stack); cudaFree(ds->wave.count);
     delete ds;
 }
 
@@ -1059,10 +1218,13 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, ds->device);
         int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, false, false>, 128, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, 0);
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
+        ds->shade_blocks = prop.multiProcessorCount * 4;
         const char* env = std::getenv("RTP_TRACE_KERNEL");
         ds->use_simple_kernel = env && std::string(env) == "simple";
+        env = std::getenv("RTP_RENDER_KERNEL");
+        ds->use_simple_render = env && std::string(env) == "simple";
         if (const char* v = std::getenv("RTP_REFILL_MIN")) ds->tune.refill_min = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_PRIM_BATCH")) ds->tune.prim_batch = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
@@ -1095,15 +1257,17 @@ static DCamera make_camera(const rtp_camera* c) {
     return d;
 }
 
-static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* d_out, bool full, bool count, Counters* counters,
-                        cudaStream_t stream) {
+// One traversal launch. out_mode: OUT_HIT / OUT_FULL / OUT_WAVE. n_dev != nullptr: the batch size is read from device memory
+// (wavefront integrator) and `n` is only an upper bound used to size the grid.
+static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* d_out, int out_mode, bool count, Counters* counters,
+                        cudaStream_t stream, const unsigned long long* n_dev = nullptr) {
     if (n == 0) return RTP_OK;
     const unsigned block = 128;
-    if (ds->use_simple_kernel) {
+    if (ds->use_simple_kernel && !n_dev && out_mode != OUT_WAVE) {
         const size_t grid = (n + block - 1) / block;
         if (grid > 0x7FFFFFFFull) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
         const dim3 g(static_cast<unsigned>(grid));
-        if (full) {
+        if (out_mode == OUT_FULL) {
             if (count) trace_closest_kernel<true, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
             else trace_closest_kernel<false, true><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
         } else {
@@ -1116,14 +1280,16 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->persistent_blocks), want)));
         WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
-#define RTP_LAUNCH_PERSISTENT(C, F, L) trace_persistent_kernel<C, F, L><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune)
-        if (list) {
-            if (full) { if (count) RTP_LAUNCH_PERSISTENT(true, true, true); else RTP_LAUNCH_PERSISTENT(false, true, true); }
-            else { if (count) RTP_LAUNCH_PERSISTENT(true, false, true); else RTP_LAUNCH_PERSISTENT(false, false, true); }
-        } else {
-            if (full) { if (count) RTP_LAUNCH_PERSISTENT(true, true, false); else RTP_LAUNCH_PERSISTENT(false, true, false); }
-            else { if (count) RTP_LAUNCH_PERSISTENT(true, false, false); else RTP_LAUNCH_PERSISTENT(false, false, false); }
-        }
+#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev)
+#define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
+    do {                                                                                             \
+        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true); else RTP_LAUNCH_PERSISTENT(false, O, true); }     \
+        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false); else RTP_LAUNCH_PERSISTENT(false, O, false); }        \
+    } while (0)
+        if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
+        else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);
+        else RTP_LAUNCH_PERSISTENT_O(OUT_HIT);
+#undef RTP_LAUNCH_PERSISTENT_O
 #undef RTP_LAUNCH_PERSISTENT
     }
     RTP_CUDA(cudaGetLastError());
@@ -1150,7 +1316,7 @@ static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hit
         const int k = static_cast<int>(chunk_id % kPipeDepth);
         cudaStream_t st = ds->streams[k];
         RTP_CUDA(cudaMemcpyAsync(ds->stage_rays[k], rays + off, m * sizeof(rtp_ray), cudaMemcpyHostToDevice, st));
-        int rc = launch_trace(ds, ds->stage_rays[k], m, ds->stage_hits[k], full, false, count ? ds->counters : nullptr, st);
+        int rc = launch_trace(ds, ds->stage_rays[k], m, ds->stage_hits[k], full ? OUT_FULL : OUT_HIT, false, count ? ds->counters : nullptr, st);
         if (rc != RTP_OK) return rc;
         ++launches;
         RTP_CUDA(cudaMemcpyAsync(static_cast<char*>(hits_out) + off * hit_bytes, ds->stage_hits[k], m * hit_bytes, cudaMemcpyDeviceToHost, st));
@@ -1184,6 +1350,27 @@ static void launch_render_paths(DeviceScene* ds, const DCamera& cam, const DRend
     else render_paths_kernel<MAXB, false><<<g, block, 0, st>>>(ds->view, cam, rp, ds->scratch, ds->counters);
 }
 
+// (re)allocates the wavefront queues for `capacity` paths per launch and a stack of `bounces` levels
+static int wave_reserve(DeviceScene* ds, size_t capacity, uint32_t bounces) {
+    WaveQueues& w = ds->wave;
+    if (w.capacity >= capacity && ds->wave_bounces >= bounces) return RTP_OK;
+    capacity = std::max(capacity, w.capacity);
+    bounces = std::max(bounces, ds->wave_bounces);
+    cudaFree(w.rays[0]); cudaFree(w.rays[1]); cudaFree(w.state[0]); cudaFree(w.state[1]); cudaFree(w.hits); cudaFree(w.stack); cudaFree(w.count);
+    w = WaveQueues{};
+    ds->wave_bounces = 0;
+    for (int k = 0; k < 2; ++k) {
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.rays[k]), capacity * sizeof(rtp_ray)));
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.state[k]), capacity * sizeof(uint4)));
+    }
+    RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.hits), capacity * sizeof(WaveHit)));
+    RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.stack), capacity * bounces * 3 * sizeof(double2)));
+    RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.count), 130 * sizeof(unsigned long long)));
+    w.capacity = capacity;
+    ds->wave_bounces = bounces;
+    return RTP_OK;
+}
+
 static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* p, double* d_rgb, double* d_fg, rtp_stats* stats,
                          cudaStream_t st) {
     DeviceScene* ds = scene->dev;
@@ -1198,9 +1385,16 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
 
     const size_t npix = static_cast<size_t>(tw) * th;
     const uint32_t ns_total = p->sample_end - p->sample_begin;
-    // samples per launch: bound the scratch buffer to ~256 MiB (8 Mi paths)
-    uint32_t per_launch = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(ns_total ? ns_total : 1, (size_t(8) << 20) / npix)));
+    // samples per launch: about 8 Mi paths (scratch 256 MiB; wavefront queues 176 B + 48 B x max_bounce per path, so the
+    // path budget shrinks for deep stacks to keep the queues under ~4 GiB)
+    const bool wave = !ds->use_simple_render;
+    const size_t path_budget = wave ? std::min<size_t>(size_t(8) << 20, (size_t(4) << 30) / (176 + 48 * static_cast<size_t>(p->max_bounce))) : (size_t(8) << 20);
+    uint32_t per_launch = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(ns_total ? ns_total : 1, path_budget / npix)));
     const size_t need = npix * per_launch;
+    if (wave && ns_total) {
+        int rc = wave_reserve(ds, need, p->max_bounce);
+        if (rc != RTP_OK) return rc;
+    }
     if (ds->scratch_elems < need) {
         cudaFree(ds->scratch); ds->scratch = nullptr; ds->scratch_elems = 0;
         RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->scratch), need * sizeof(double4)));
@@ -1227,13 +1421,30 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
         rp.sample_begin = p->sample_begin + s0;
         rp.n_samples = std::min(per_launch, ns_total - s0);
         const size_t total = npix * rp.n_samples;
-        if (p->max_bounce <= 8) launch_render_paths<8>(ds, cam, rp, total, count, st);
-        else if (p->max_bounce <= 32) launch_render_paths<32>(ds, cam, rp, total, count, st);
-        else launch_render_paths<128>(ds, cam, rp, total, count, st);
-        RTP_CUDA(cudaGetLastError());
+        if (wave) {
+            // generate -> (trace -> shade) x max_bounce; queue sizes stay on the device
+            RTP_CUDA(cudaMemsetAsync(ds->wave.count, 0, 130 * sizeof(unsigned long long), st));
+            wave_generate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(cam, rp, ds->wave, total);
+            RTP_CUDA(cudaGetLastError());
+            ++launches;
+            const unsigned shade_grid = static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->shade_blocks), (total + 255) / 256));
+            for (uint32_t b = 0; b < p->max_bounce; ++b) {
+                int rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, ds->wave.count + b);
+                if (rc != RTP_OK) return rc;
+                wave_shade_kernel<<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch);
+                RTP_CUDA(cudaGetLastError());
+                launches += 2;
+            }
+        } else {
+            if (p->max_bounce <= 8) launch_render_paths<8>(ds, cam, rp, total, count, st);
+            else if (p->max_bounce <= 32) launch_render_paths<32>(ds, cam, rp, total, count, st);
+            else launch_render_paths<128>(ds, cam, rp, total, count, st);
+            RTP_CUDA(cudaGetLastError());
+            ++launches;
+        }
         resolve_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, st>>>(ds->scratch, ds->acc, npix, rp.n_samples, first ? 1 : 0);
         RTP_CUDA(cudaGetLastError());
-        launches += 2;
+        ++launches;
         first = false;
     }
     const double divisor = (p->flags & RTP_RENDER_RAW_SUMS) ? 0.0 : static_cast<double>(p->num_samples);
@@ -1382,7 +1593,7 @@ int rtp_trace_closest_full(rtp_scene* scene, const rtp_ray* rays, size_t n, rtp_
 int rtp_trace_closest_device(rtp_scene* scene, const rtp_ray* d_rays, size_t n, rtp_hit* d_hits_out, void* cuda_stream) {
     if (!scene || (n && (!d_rays || !d_hits_out))) return set_error(RTP_ERR_INVALID, "null argument");
     RTP_CUDA(cudaSetDevice(scene->dev->device));
-    return launch_trace(scene->dev, d_rays, n, d_hits_out, false, false, nullptr, static_cast<cudaStream_t>(cuda_stream));
+    return launch_trace(scene->dev, d_rays, n, d_hits_out, OUT_HIT, false, nullptr, static_cast<cudaStream_t>(cuda_stream));
 }
 
 /* Counting variant used by tests and the roofline report: node visits / primitive tests for a device-resident batch. */
@@ -1394,7 +1605,7 @@ int rtp_trace_closest_device_counted(rtp_scene* scene, const rtp_ray* d_rays, si
     cudaStream_t st = ds->streams[0];
     RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), st));
     RTP_CUDA(cudaEventRecord(ds->ev_begin, st));
-    int rc = launch_trace(ds, d_rays, n, d_hits_out, false, true, ds->counters, st);
+    int rc = launch_trace(ds, d_rays, n, d_hits_out, OUT_HIT, true, ds->counters, st);
     if (rc != RTP_OK) return rc;
     RTP_CUDA(cudaEventRecord(ds->ev_end, st));
     RTP_CUDA(cudaEventSynchronize(ds->ev_end));

@@ -245,6 +245,22 @@ def test_c1_config_reduced_spp(gpu):
     assert sg.rays == so.rays or rep["differing"] > 0
 
 
+@pytest.mark.parametrize("name,depth", [("demo", 8), ("glass_bunny", 1), ("glass_bunny", 2), ("glass_bunny", 12), ("bunny_lambert", 40), ("three_balls", 3)])
+def test_wavefront_equals_one_thread_per_path_integrator(gpu, monkeypatch, name, depth):
+    """the wavefront integrator (queues in HBM, persistent traversal, f32 culling) and the baseline one-thread-per-path kernel
+    (exact f64 walk) are two implementations of main.rs:70-83: every pixel, the foreground mask and the ray count agree bit for bit"""
+    sc = getattr(scenes, name)()
+    g = api.Scene(sc)
+    iw, fw, sw = g.render(160, 90, 3, max_bounce=depth, seed=7)
+    monkeypatch.setenv("RTP_RENDER_KERNEL", "simple")
+    gs = api.Scene(sc)
+    monkeypatch.delenv("RTP_RENDER_KERNEL")
+    i1, f1, s1 = gs.render(160, 90, 3, max_bounce=depth, seed=7)
+    assert iw.tobytes() == i1.tobytes() and fw.tobytes() == f1.tobytes()
+    assert sw.rays == s1.rays and sw.paths == s1.paths
+    g.close(); gs.close()
+
+
 def test_tiles_and_sample_ranges(gpu):
     sc = scenes.bunny_lambert()
     g = api.Scene(sc)
