@@ -117,30 +117,30 @@ __device__ __noinline__ bool collide_literal_slow(const DNode* __restrict__ node
     return collide_literal(ldg2(nb), ldg2(nb + 2), ldg2(nb + 4), mk(ox, oy, oz), mk(ix, iy, iz), tmin, T);
 }
 
-// Conservative f32 culling. Inputs: the node's outward-inflated f32 box (rtp_internal.h DNode32), inv32 = RN32(1/d),
-// and per axis c_lo = RD32(-(o*inv) - K), c_hi = RU32(-(o*inv) + K) with K = 2^-21 |o*inv| + 1e-37. Then
+// Conservative f32 culling. Inputs: a child's outward-inflated f32 box (rtp_internal.h DWide), inv32 = RN32(1/d), and per
+// axis c_lo = RD32(-(o*inv) - K), c_hi = RU32(-(o*inv) + K) with K = 2^-21 |o*inv| + 1e-37. Then
 //   n_lo = fma(near_plane, inv32, c_lo) <= the f64 slab entry (min-o)*inv as the reference rounds it, and
 //   f_hi = fma(far_plane,  inv32, c_hi) >= the f64 slab exit,
 // for |o|, |box| <= 1e15 and 1e-15 <= |inv| <= 1e15 (no overflow/underflow trouble); the derivation is in DESIGN.md §4.
 // With T_up >= t_max and tmin_dn <= t_min, `min(T_up, f_hi) < max(tmin_dn, n_lo)` therefore implies that the reference's
 // f64 test `t_max >= t_min` is false for this box and for every box inside it: the subtree can be skipped. The converse
-// is not claimed: a node that is not rejected here is simply visited, and leaves get the exact f64 gate.
+// is not claimed: a child that is not rejected here is simply visited, and leaves get the exact f64 gate.
 struct Ray32 {
     float ix, iy, iz;
     float clx, cly, clz, chx, chy, chz;
     float tmin_dn, T_up;
 };
 
-__device__ __forceinline__ bool collide32_reject(const float4 q0, const float2 q1, const Ray32& r, bool sx, bool sy, bool sz) {
-    // q0 = (min.x, min.y, min.z, max.x), q1 = (max.y, max.z)
-    const float pnx = sx ? q0.w : q0.x, pfx = sx ? q0.x : q0.w;
-    const float pny = sy ? q1.x : q0.y, pfy = sy ? q0.y : q1.x;
-    const float pnz = sz ? q1.y : q0.z, pfz = sz ? q0.z : q1.y;
-    const float nx = fmaf(pnx, r.ix, r.clx), ny = fmaf(pny, r.iy, r.cly), nz = fmaf(pnz, r.iz, r.clz);
-    const float fx = fmaf(pfx, r.ix, r.chx), fy = fmaf(pfy, r.iy, r.chy), fz = fmaf(pfz, r.iz, r.chz);
-    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, r.tmin_dn));
-    const float tf = fminf(fminf(fx, fy), fminf(fz, r.T_up));
-    return tf < tn;
+// the four children of one DWide node at once: bit k of the result = child k is NOT rejected
+__device__ __forceinline__ uint32_t collide32_wide(const float4 nx4, const float4 fx4, const float4 ny4, const float4 fy4, const float4 nz4,
+                                                   const float4 fz4, const Ray32& r) {
+#define RTP_CHILD(c)                                                                                                        \
+    (fminf(fminf(fmaf(fx4.c, r.ix, r.chx), fmaf(fy4.c, r.iy, r.chy)), fminf(fmaf(fz4.c, r.iz, r.chz), r.T_up)) >=          \
+     fmaxf(fmaxf(fmaf(nx4.c, r.ix, r.clx), fmaf(ny4.c, r.iy, r.cly)), fmaxf(fmaf(nz4.c, r.iz, r.clz), r.tmin_dn)))
+    // `>=` on finite-or-infinite operands is exactly !(tf < tn); no NaN can occur for an f32-eligible ray (finite inv, finite
+    // or infinite planes of one sign per product)
+    return (RTP_CHILD(x) ? 1u : 0u) | (RTP_CHILD(y) ? 2u : 0u) | (RTP_CHILD(z) ? 4u : 0u) | (RTP_CHILD(w) ? 8u : 0u);
+#undef RTP_CHILD
 }
 
 __device__ __forceinline__ bool in_f32_range(double x) { const double a = fabs(x); return a >= 1e-15 && a <= 1e15; }
@@ -422,13 +422,23 @@ struct Tuning {
     int f32_culling; // 1: eligible rays cull with the conservative f32 walk
 };
 
-// Per-lane traversal state shared by the ray-batch kernel and the path integrator.
+// Per-lane traversal state.
+//   f32-eligible lanes (m32) walk the 4-wide culling tree: `next` = node to visit, (cur, pend, c0..c3) = node whose
+//   children are being handed out, pending-children mask and its child words; a short stack of (node << 4 | mask)
+//   entries in shared memory holds the ancestors that still have pending children.
+//   Other lanes (non-finite or axis-parallel rays, huge coordinates, List roots) walk the exact f64 pre-order tree with
+//   `next` as the pre-order index (bvh.rs:93-119 literally).
+constexpr uint32_t kEnd = 0xFFFFFFFFu;   // `next`: the walk is over
+constexpr uint32_t kNone = 0xFFFFFFFEu;  // `next`: no node to visit, take the next pending child
 struct Walker {
     D3 o, d, inv;
     double tmin;
     HitRec h;        // h.t is the running t_max
     Ray32 r32;
-    uint32_t node;   // pre-order index, END when the walk is over
+    uint32_t next;
+    uint32_t cur, pend, sp;
+    uint32_t c0, c1, c2, c3;
+    uint32_t onx, ony, onz;  // byte offset of the near plane inside each axis block of a DWide (0 or 16)
     uint32_t prim;   // kNoPrim, or slot | kind << 31 of the leaf the lane is parked at
     bool fast;       // eligible for collide_fast (finite, non-axis-parallel, no NaN)
     bool m32;        // eligible for the f32 culling walk
@@ -455,40 +465,71 @@ __device__ __forceinline__ void walker_start(Walker& w, const DSceneView& sc, co
         w.r32.chx = __double2float_ru(-px + kx); w.r32.chy = __double2float_ru(-py + ky); w.r32.chz = __double2float_ru(-pz + kz);
         w.r32.tmin_dn = __double2float_rd(tmin);
         w.r32.T_up = __double2float_ru(tmax);
+        w.onx = w.sx ? 16u : 0u; w.ony = w.sy ? 16u : 0u; w.onz = w.sz ? 16u : 0u;
     }
-    w.node = 0;
+    w.next = 0;
+    w.pend = 0; w.sp = 0; w.cur = 0;
     w.prim = kNoPrim;
     w.need_gate = false;
 }
 
-// One culling step of an f32-eligible lane (node != END, not parked).
+// One step of an f32-eligible lane that is walking (next != kEnd, not parked): visit `next` if there is one (four
+// conservative slab tests), then hand out the next pending child in rank order: a leaf parks the lane, an internal
+// child becomes `next`. `stack` is this thread's column of the shared-memory stack (stride = blockDim.x).
 template <bool COUNT>
-__device__ __forceinline__ void walker_step32(Walker& w, const DSceneView& sc, LocalCounters& lc) {
-    const float4* np = reinterpret_cast<const float4*>(sc.nodes32 + w.node);
-    const float4 q0 = __ldg(np);
-    const float4 q1 = __ldg(np + 1);
-    const bool reject = collide32_reject(q0, make_float2(q1.x, q1.y), w.r32, w.sx, w.sy, w.sz);
-    if (COUNT) {
-        lc.node_visits++;
-        if (reject) {  // the conservative test must never reject a box the exact test accepts
-            const double* nb = sc.nodes[w.node].bmin;
-            if (collide_literal(ldg2(nb), ldg2(nb + 2), ldg2(nb + 4), w.o, w.inv, w.tmin, w.h.t)) lc.violations++;
+__device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc, LocalCounters& lc, uint32_t* __restrict__ stack, uint32_t stride) {
+    if (w.next != kNone) {
+        const char* np = reinterpret_cast<const char*>(sc.wide + w.next);
+        const float4 nx4 = __ldg(reinterpret_cast<const float4*>(np + w.onx));
+        const float4 fx4 = __ldg(reinterpret_cast<const float4*>(np + (16u - w.onx)));
+        const float4 ny4 = __ldg(reinterpret_cast<const float4*>(np + 32u + w.ony));
+        const float4 fy4 = __ldg(reinterpret_cast<const float4*>(np + 32u + (16u - w.ony)));
+        const float4 nz4 = __ldg(reinterpret_cast<const float4*>(np + 64u + w.onz));
+        const float4 fz4 = __ldg(reinterpret_cast<const float4*>(np + 64u + (16u - w.onz)));
+        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 96u));
+        w.pend = collide32_wide(nx4, fx4, ny4, fy4, nz4, fz4, w.r32);
+        if (COUNT) {
+            lc.node_visits++;
+            const double* b64 = sc.wide_boxes + static_cast<size_t>(w.next) * 24;
+            for (uint32_t k = 0; k < 4; ++k)  // the conservative test must never reject a box the exact test accepts
+                if (!((w.pend >> k) & 1u) && (&ch.x)[k] != kWideEmpty &&
+                    collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), w.o, w.inv, w.tmin, w.h.t))
+                    lc.violations++;
         }
+        w.c0 = ch.x; w.c1 = ch.y; w.c2 = ch.z; w.c3 = ch.w;
+        w.cur = w.next;
+        w.next = kNone;
     }
-    const uint32_t skip = __float_as_uint(q1.z), leaf = __float_as_uint(q1.w);
-    w.node = reject ? skip : w.node + 1;
-    if (!reject & (leaf != kNoPrim)) { w.prim = leaf; w.need_gate = true; }
+    if (w.pend == 0u) {
+        if (w.sp == 0u) { w.next = kEnd; return; }
+        w.sp -= 1u;
+        const uint32_t e = stack[w.sp * stride];
+        w.cur = e >> 4; w.pend = e & 15u;
+        const uint4 ch = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(sc.wide + w.cur) + 96u));
+        w.c0 = ch.x; w.c1 = ch.y; w.c2 = ch.z; w.c3 = ch.w;
+    }
+    const uint32_t k = __ffs(w.pend) - 1u;
+    w.pend &= w.pend - 1u;
+    const uint32_t c = k == 0u ? w.c0 : (k == 1u ? w.c1 : (k == 2u ? w.c2 : w.c3));
+    if (c & kWideLeaf) {
+        w.prim = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+        w.need_gate = true;
+    } else {
+        if (w.pend) { stack[w.sp * stride] = (w.cur << 4) | w.pend; w.sp += 1u; }
+        w.next = c;
+    }
 }
 
 // One exact f64 step for lanes outside the f32 path's preconditions (bvh.rs:93-119 literally, or collide_fast).
 template <bool COUNT>
 __device__ __forceinline__ void walker_step64(Walker& w, const DSceneView& sc, LocalCounters& lc) {
-    const double* nb = sc.nodes[w.node].bmin;
+    const double* nb = sc.nodes[w.next].bmin;
     const double2 b0 = ldg2(nb), b1 = ldg2(nb + 2), b2 = ldg2(nb + 4);
     const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nb + 6));
     if (COUNT) lc.node_visits++;
     const bool pass = w.fast ? collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, w.h.t) : collide_literal(b0, b1, b2, w.o, w.inv, w.tmin, w.h.t);
-    w.node = pass ? w.node + 1 : meta.x;
+    w.next = pass ? w.next + 1 : meta.x;
+    if (w.next >= sc.n_nodes) w.next = kEnd;
     if (pass & (meta.y != kNoPrim)) { w.prim = meta.y | (meta.z << 31); w.need_gate = false; }
 }
 
@@ -516,7 +557,9 @@ __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, Loc
         if (hit) {  // bvh.rs:107-111: shrink t_max, later hit replaces
             w.h.t = t; w.h.u = u; w.h.v = v; w.h.slot = slot; w.h.kind = kind;
             w.r32.T_up = __double2float_ru(t);
-            if (!(t == t)) { w.fast = false; w.m32 = false; }  // NaN t (non-finite geometry only): back to the literal test
+            // NaN t: only with overflowing (> 1e150) geometry, which the f32 walk's preconditions (|coordinates| <= 1e15) exclude;
+            // a lane of the exact walk drops back to the literal slab test, whose NaN rules are the reference's
+            if (!(t == t)) w.fast = false;
         }
     }
     w.prim = kNoPrim;
@@ -525,19 +568,21 @@ __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, Loc
 template <bool COUNT, int OUT, bool LIST>
 __global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev) {
+    extern __shared__ uint32_t wide_stack[];  // [level][thread]
     if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t END = LIST ? sc.n_prims : sc.n_nodes;  // List roots walk the primitive run without slab gates
+    uint32_t* const my_stack = wide_stack + threadIdx.x;
+    const uint32_t stride = blockDim.x;
     constexpr size_t kNoRay = ~static_cast<size_t>(0);
     LocalCounters lc = {0, 0, 0, 0, 0, 0};
 
-    // lane state: node == END && prim == kNoPrim  -> empty (its finished ray, if any, is written at the next refill);
-    //             prim != kNoPrim                 -> parked at a leaf;  otherwise walking
+    // lane state: next == kEnd && prim == kNoPrim  -> empty (its finished ray, if any, is written at the next refill);
+    //             prim != kNoPrim                  -> parked at a leaf;  otherwise walking
     Walker w;
     w.o = w.d = w.inv = mk(0, 0, 0);
     w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
-    w.node = END; w.prim = kNoPrim;
+    w.next = kEnd; w.prim = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
     w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
     w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     size_t idx = kNoRay;
@@ -545,7 +590,7 @@ __global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc,
 
     for (;;) {
         // ---- retire finished rays and refill ----------------------------------------------------------
-        const bool is_empty = (w.node == END) & (w.prim == kNoPrim);
+        const bool is_empty = (w.next == kEnd) & (w.prim == kNoPrim);
         const unsigned empty = __ballot_sync(0xffffffffu, is_empty);
         if (empty == 0xffffffffu || (more && __popc(empty) >= tune.refill_min)) {
             if (is_empty && idx != kNoRay) {
@@ -565,23 +610,26 @@ __global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc,
                     const double2* rp = reinterpret_cast<const double2*>(rays + i);
                     const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
                     walker_start(w, sc, tune, mk(r0.x, r0.y, r1.x), mk(r1.y, r2.x, r2.y), r3.x, r3.y);
-                    if (END == 0) w.node = END;
+                    if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
                     lc.rays++;
                 }
             }
-            if (__ballot_sync(0xffffffffu, w.node != END) == 0u) continue;
+            if (__ballot_sync(0xffffffffu, w.next != kEnd) == 0u) continue;
         }
 
         if (LIST) {
             // hittable.rs:110-120: every primitive, in caller order, no boxes
-            if (w.node != END) { w.prim = w.node | (__ldg(&sc.nodes[w.node].kind) << 31); w.need_gate = false; w.node = w.node + 1; }
+            if (w.next != kEnd) {
+                w.prim = w.next | (__ldg(&sc.nodes[w.next].kind) << 31); w.need_gate = false;
+                w.next = w.next + 1 < sc.n_prims ? w.next + 1 : kEnd;
+            }
         } else {
-            // ---- hot walk: f32-eligible lanes visit up to two nodes per vote -------------------------------
+            // ---- hot walk: f32-eligible lanes take up to two steps per vote -----------------------------------
             for (;;) {
 #pragma unroll
                 for (int rep = 0; rep < 2; ++rep)
-                    if ((w.node != END) & (w.prim == kNoPrim) & w.m32) walker_step32<COUNT>(w, sc, lc);
-                const unsigned walking = __ballot_sync(0xffffffffu, (w.node != END) & (w.prim == kNoPrim) & w.m32);
+                    if ((w.next != kEnd) & (w.prim == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
+                const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim == kNoPrim) & w.m32);
                 if (walking == 0u) break;
                 const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
                 if (__popc(parked) >= tune.prim_batch) break;
@@ -589,7 +637,7 @@ __global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc,
             }
             // ---- lanes outside the f32 path's preconditions take one exact step per round ------------------
             if (__any_sync(0xffffffffu, !w.m32)) {
-                if ((w.node != END) & (w.prim == kNoPrim) & !w.m32) walker_step64<COUNT>(w, sc, lc);
+                if ((w.next != kEnd) & (w.prim == kNoPrim) & !w.m32) walker_step64<COUNT>(w, sc, lc);
             }
         }
 
@@ -1124,7 +1172,9 @@ constexpr size_t kChunkRays = 1u << 18;  // 16 MiB of rays per pipeline stage
 struct DeviceScene {
     int device = 0;
     DNode* nodes = nullptr;
-    DNode32* nodes32 = nullptr;
+    DWide* wide = nullptr;
+    double* wide_boxes = nullptr;
+    size_t stack_bytes = 0;            // dynamic shared memory of the persistent kernels: wide_depth x 128 threads x 4 B
     DPrim* prims = nullptr;
     DAttr* attrs = nullptr;
     DMaterial* materials = nullptr;
@@ -1164,7 +1214,7 @@ static int upload(const std::vector<T>& v, T** out, uint64_t* bytes) {
 
 void device_scene_free(DeviceScene* ds) {
     if (!ds) return;
-    cudaFree(ds->nodes); cudaFree(ds->nodes32); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
+    cudaFree(ds->nodes); cudaFree(ds->wide); cudaFree(ds->wide_boxes); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
     for (uint8_t* p : ds->images) cudaFree(p);
     cudaFree(ds->counters);
     cudaFree(ds->queues);
@@ -1196,7 +1246,9 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     ds->device = g_device;
     auto bail = [&](int code) { device_scene_free(ds); return code; };
     if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
-    if ((rc = upload(flat.nodes32, &ds->nodes32, &ds->bytes)) != RTP_OK) return bail(rc);
+    if ((rc = upload(flat.wide, &ds->wide, &ds->bytes)) != RTP_OK) return bail(rc);
+    if ((rc = upload(flat.wide_boxes, &ds->wide_boxes, &ds->bytes)) != RTP_OK) return bail(rc);
+    ds->stack_bytes = static_cast<size_t>(std::max<uint32_t>(flat.wide_depth, 1u)) * 128 * sizeof(uint32_t);
     if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.materials, &ds->materials, &ds->bytes)) != RTP_OK) return bail(rc);
@@ -1218,7 +1270,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, ds->device);
         int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, ds->stack_bytes);
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 4;
         const char* env = std::getenv("RTP_TRACE_KERNEL");
@@ -1237,8 +1289,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     if (e != cudaSuccess) return bail(set_error(RTP_ERR_CUDA, std::string("scene resources: ") + cudaGetErrorString(e)));
 
     DSceneView& v = ds->view;
-    v.nodes = ds->nodes; v.nodes32 = ds->nodes32; v.prims = ds->prims;
-    v.f32_culling = (flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15) ? 1u : 0u; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
+    v.nodes = ds->nodes; v.wide = ds->wide; v.wide_boxes = ds->wide_boxes; v.prims = ds->prims;
+    v.f32_culling = (flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96) ? 1u : 0u; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
     v.n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
     v.n_prims = static_cast<uint32_t>(flat.prims.size());
     v.root_kind = flat.root_kind;
@@ -1280,7 +1332,7 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->persistent_blocks), want)));
         WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
-#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev)
+#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev)
 #define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
     do {                                                                                             \
         if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true); else RTP_LAUNCH_PERSISTENT(false, O, true); }     \
@@ -1525,7 +1577,8 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
         s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? s->flat.n_reference_nodes : 0u;
         // the host copies of the big arrays are no longer needed
         std::vector<DNode>().swap(s->flat.nodes);
-        std::vector<DNode32>().swap(s->flat.nodes32);
+        std::vector<DWide>().swap(s->flat.wide);
+        std::vector<double>().swap(s->flat.wide_boxes);
         std::vector<DPrim>().swap(s->flat.prims);
         std::vector<DAttr>().swap(s->flat.attrs);
         std::vector<std::vector<uint8_t>>().swap(s->flat.images);

@@ -183,6 +183,98 @@ struct SeqBuilder {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// 4-wide f32 culling tree (rtp_internal.h DWide), collapsed from the binary pre-order tree in `nodes`: a node starts with
+// its two binary children and repeatedly replaces the internal child of largest surface area by that child's two
+// children, in place, until it has four children or only leaves. In-place replacement keeps the children in rank order,
+// so visiting children left to right meets the leaves in the reference's depth-first order.
+// ---------------------------------------------------------------------------------------------
+static void round_out(const double* bmin, const double* bmax, float* lo, float* hi) {
+    for (int a = 0; a < 3; ++a) {
+        const double mag = std::fmax(std::fabs(bmin[a]), std::fabs(bmax[a]));
+        const double r = std::ldexp(mag, -21);
+        float l = static_cast<float>(bmin[a] - r), h = static_cast<float>(bmax[a] + r);
+        if (static_cast<double>(l) > bmin[a] - r) l = std::nextafterf(l, -std::numeric_limits<float>::infinity());
+        if (static_cast<double>(h) < bmax[a] + r) h = std::nextafterf(h, std::numeric_limits<float>::infinity());
+        lo[a] = l; hi[a] = h;
+    }
+}
+
+static void build_wide(FlatScene* out) {
+    const std::vector<DNode>& bn = out->nodes;
+    std::vector<DWide>& wide = out->wide;
+    std::vector<double>& boxes = out->wide_boxes;
+    wide.clear(); boxes.clear();
+    out->wide_depth = 0;
+    auto half_area = [&](uint32_t b) {
+        const double dx = bn[b].bmax[0] - bn[b].bmin[0], dy = bn[b].bmax[1] - bn[b].bmin[1], dz = bn[b].bmax[2] - bn[b].bmin[2];
+        const double a = dx * dy + dy * dz + dz * dx;
+        return a == a ? a : std::numeric_limits<double>::infinity();
+    };
+    struct Todo { uint32_t bnode, wnode, depth; };
+    std::vector<Todo> todo;
+    wide.emplace_back();
+    todo.push_back({0u, 0u, 1u});
+    while (!todo.empty()) {
+        const Todo t = todo.back();
+        todo.pop_back();
+        out->wide_depth = std::max(out->wide_depth, t.depth);
+        uint32_t kids[4];
+        int nk = 0;
+        if (bn[t.bnode].prim != kNoPrim) {
+            kids[nk++] = t.bnode;  // a one-leaf scene: the root holds that leaf as its only child
+        } else {
+            kids[nk++] = t.bnode + 1;
+            kids[nk++] = bn[t.bnode + 1].skip;
+            while (nk < 4) {
+                int pick = -1;
+                double best = -1.0;
+                for (int k = 0; k < nk; ++k)
+                    if (bn[kids[k]].prim == kNoPrim) {
+                        const double a = half_area(kids[k]);
+                        if (a > best) { best = a; pick = k; }
+                    }
+                if (pick < 0) break;
+                const uint32_t b = kids[pick];
+                for (int k = nk; k > pick + 1; --k) kids[k] = kids[k - 1];
+                kids[pick] = b + 1;
+                kids[pick + 1] = bn[b + 1].skip;
+                ++nk;
+            }
+        }
+        DWide w;
+        std::memset(&w, 0, sizeof w);
+        double b64[4][6];
+        for (int k = 0; k < 4; ++k) {
+            if (k < nk) {
+                const DNode& c = bn[kids[k]];
+                float lo[3], hi[3];
+                round_out(c.bmin, c.bmax, lo, hi);
+                for (int a = 0; a < 3; ++a) { w.plane[a][0][k] = lo[a]; w.plane[a][1][k] = hi[a]; b64[k][a] = c.bmin[a]; b64[k][3 + a] = c.bmax[a]; }
+                if (c.prim != kNoPrim) {
+                    w.child[k] = kWideLeaf | (c.kind << 30) | c.prim;
+                } else {
+                    const uint32_t wi = static_cast<uint32_t>(wide.size());
+                    wide.emplace_back();
+                    w.child[k] = wi;
+                    todo.push_back({kids[k], wi, t.depth + 1});
+                }
+            } else {
+                for (int a = 0; a < 3; ++a) {
+                    w.plane[a][0][k] = std::numeric_limits<float>::infinity();
+                    w.plane[a][1][k] = -std::numeric_limits<float>::infinity();
+                    b64[k][a] = std::numeric_limits<double>::infinity(); b64[k][3 + a] = -std::numeric_limits<double>::infinity();
+                }
+                w.child[k] = kWideEmpty;
+            }
+        }
+        wide[t.wnode] = w;
+        if (boxes.size() < wide.size() * 24) boxes.resize(wide.size() * 24);
+        std::memcpy(&boxes[static_cast<size_t>(t.wnode) * 24], b64, sizeof b64);
+    }
+    boxes.resize(wide.size() * 24);
+}
+
 static bool emit_ok(const rtp_emit& e, uint32_t n_textures) {
     if (e.kind > RTP_EMIT_SKY_SPHERE) return false;
     return e.kind != RTP_EMIT_SKY_SPHERE || e.texture < n_textures;
@@ -197,7 +289,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
         return set_error(RTP_ERR_INVALID, "null table with non-zero count");
     if (d->root_kind == RTP_ROOT_BVH && d->n_hittables == 0)
         return set_error(RTP_ERR_INVALID, "Bvh::new on an empty list is unreachable!() in the reference (bvh.rs:40)");
-    if (d->n_hittables >= 0x7FFFFFFFu) return set_error(RTP_ERR_INVALID, "too many hittables");
+    if (d->n_hittables >= 0x3FFFFFFFu) return set_error(RTP_ERR_INVALID, "too many hittables");
 
     // ---- tables -------------------------------------------------------------------------
     out->root_kind = d->root_kind;
@@ -344,22 +436,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
     if (d->root_kind == RTP_ROOT_BVH) {
         for (DNode& nd : out->nodes)
             if (nd.prim != kNoPrim) nd.kind = d->hittables[items[nd.prim].id].kind;
-        // f32 culling copy: outward rounding + 2^-21 relative inflation (error budget in DESIGN.md §4)
-        out->nodes32.resize(out->nodes.size());
-        for (size_t k = 0; k < out->nodes.size(); ++k) {
-            const DNode& nd = out->nodes[k];
-            DNode32& q = out->nodes32[k];
-            for (int a = 0; a < 3; ++a) {
-                const double mag = std::fmax(std::fabs(nd.bmin[a]), std::fabs(nd.bmax[a]));
-                const double r = std::ldexp(mag, -21);
-                float lo = static_cast<float>(nd.bmin[a] - r), hi = static_cast<float>(nd.bmax[a] + r);
-                if (static_cast<double>(lo) > nd.bmin[a] - r) lo = std::nextafterf(lo, -std::numeric_limits<float>::infinity());
-                if (static_cast<double>(hi) < nd.bmax[a] + r) hi = std::nextafterf(hi, std::numeric_limits<float>::infinity());
-                q.bmin[a] = lo; q.bmax[a] = hi;
-            }
-            q.skip = nd.skip;
-            q.prim = nd.prim == kNoPrim ? kNoPrim : (nd.prim | (nd.kind << 31));
-        }
+        build_wide(out);
     } else {
         // a List root is traversed as a flat run of leaves without slab tests; nodes carry only the kind
         out->nodes.assign(n ? n : 1, DNode{});

@@ -48,17 +48,21 @@ struct alignas(16) DPrim {  // 128 B
 };
 static_assert(sizeof(DPrim) == 128, "DPrim must be 128 bytes");
 
-// Culling node in f32: the node's f64 box rounded OUTWARD and inflated by 2^-21 * max(|min|,|max|)
-// per axis, so that an f32 slab evaluation with the matching ray-side slack is a rigorous lower /
-// upper bound of the f64 evaluation (rtp_device.cu, collide32_reject). Same pre-order
-// index space as DNode. prim: kNoPrim for branches, slot | kind << 31 for leaves.
-struct alignas(32) DNode32 {  // 32 B
-    float bmin[3];
-    float bmax[3];
-    uint32_t skip;
-    uint32_t prim;
+// Culling tree in f32: a 4-wide tree over the rank-ordered leaf sequence. A node holds the boxes of its (up to) four
+// children, in rank order, as six 4-lane planes (structure of arrays), so one 128-byte line answers four slab tests and a
+// ray picks its near / far planes by ADDRESS (offset 0 or 16 inside each axis block) instead of by select. Every child box is
+// the child's exact f64 box rounded OUTWARD and inflated by 2^-21 * max(|min|,|max|) per axis, so that an f32 slab
+// evaluation with the matching ray-side slack is a rigorous lower / upper bound of the reference's f64 evaluation
+// (rtp_device.cu collide32). child[k]: internal = index of the child node; leaf = kWideLeaf | kind << 30 |
+// primitive slot; unused = kWideEmpty with an inverted (+inf, -inf) box that no ray can enter.
+constexpr uint32_t kWideLeaf = 0x80000000u;
+constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
+struct alignas(128) DWide {  // 128 B = one L1/L2 line
+    float plane[3][2][4];    // [axis][0 = min, 1 = max][child]
+    uint32_t child[4];
+    uint32_t _pad[4];
 };
-static_assert(sizeof(DNode32) == 32, "DNode32 must be 32 bytes");
+static_assert(sizeof(DWide) == 128, "DWide must be 128 bytes");
 
 // Shading attributes of a triangle (mesh.rs:7-11 normals/uvs of its three vertices), read once
 // per accepted path vertex, never during traversal.
@@ -89,7 +93,8 @@ struct DMaterial {
 
 struct DSceneView {  // passed by value to kernels
     const DNode* nodes;
-    const DNode32* nodes32;
+    const DWide* wide;
+    const double* wide_boxes;  // [node][child][min xyz, max xyz] exact f64 child boxes (counting kernels: violation check)
     const DPrim* prims;
     const DAttr* attrs;
     const DMaterial* materials;
@@ -108,7 +113,9 @@ struct DSceneView {  // passed by value to kernels
 // ---------------------------------------------------------------------------------------------
 struct FlatScene {
     std::vector<DNode> nodes;
-    std::vector<DNode32> nodes32;
+    std::vector<DWide> wide;
+    std::vector<double> wide_boxes;
+    uint32_t wide_depth = 0;         // nodes on the longest root-to-leaf path of the 4-wide tree
     std::vector<DPrim> prims;
     std::vector<DAttr> attrs;
     std::vector<DMaterial> materials;
