@@ -313,7 +313,7 @@ struct alignas(16) WaveHit {
 };
 static_assert(sizeof(WaveHit) == 32, "WaveHit must be 32 bytes");
 
-enum { OUT_HIT = 0, OUT_FULL = 1, OUT_WAVE = 2 };
+enum { OUT_HIT = 0, OUT_FULL = 1, OUT_WAVE = 2, OUT_TAIL = 3 };
 
 template <int OUT>
 __device__ __forceinline__ void write_hit(const DSceneView& sc, void* __restrict__ out, size_t i, D3 o, D3 d, const HitRec& h) {
@@ -420,6 +420,8 @@ struct Tuning {
     int prim_batch;  // run primitive tests when at least this many lanes are parked at a leaf
     int fast_slab;   // 1: eligible rays use collide_fast
     int f32_culling; // 1: eligible rays cull with the conservative f32 walk
+    int walk_reps;   // culling-tree steps per warp vote
+    int min_lanes;   // smallest number of rays a warp holds when the batch is small
 };
 
 // Per-lane traversal state.
@@ -563,99 +565,6 @@ __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, Loc
         }
     }
     w.prim = kNoPrim;
-}
-
-template <bool COUNT, int OUT, bool LIST>
-__global__ void __launch_bounds__(128, 5) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
-                                                                  Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev) {
-    extern __shared__ uint32_t wide_stack[];  // [level][thread]
-    if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    uint32_t* const my_stack = wide_stack + threadIdx.x;
-    const uint32_t stride = blockDim.x;
-    constexpr size_t kNoRay = ~static_cast<size_t>(0);
-    LocalCounters lc = {0, 0, 0, 0, 0, 0};
-
-    // lane state: next == kEnd && prim == kNoPrim  -> empty (its finished ray, if any, is written at the next refill);
-    //             prim != kNoPrim                  -> parked at a leaf;  otherwise walking
-    Walker w;
-    w.o = w.d = w.inv = mk(0, 0, 0);
-    w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
-    w.next = kEnd; w.prim = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
-    w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
-    w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    size_t idx = kNoRay;
-    bool more = true;  // warp-uniform: the queue may still hold rays
-
-    for (;;) {
-        // ---- retire finished rays and refill ----------------------------------------------------------
-        const bool is_empty = (w.next == kEnd) & (w.prim == kNoPrim);
-        const unsigned empty = __ballot_sync(0xffffffffu, is_empty);
-        if (empty == 0xffffffffu || (more && __popc(empty) >= tune.refill_min)) {
-            if (is_empty && idx != kNoRay) {
-                write_hit<OUT>(sc, out, idx, w.o, w.d, w.h);
-                idx = kNoRay;
-            }
-            if (!more) break;  // every lane is empty and the queue is drained
-            const int cnt = __popc(empty), leader = __ffs(empty) - 1;
-            unsigned long long base = 0;
-            if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
-            if (is_empty) {
-                const size_t i = static_cast<size_t>(base) + __popc(empty & lt_mask);
-                if (i < n) {
-                    idx = i;
-                    const double2* rp = reinterpret_cast<const double2*>(rays + i);
-                    const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-                    walker_start(w, sc, tune, mk(r0.x, r0.y, r1.x), mk(r1.y, r2.x, r2.y), r3.x, r3.y);
-                    if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
-                    lc.rays++;
-                }
-            }
-            if (__ballot_sync(0xffffffffu, w.next != kEnd) == 0u) continue;
-        }
-
-        if (LIST) {
-            // hittable.rs:110-120: every primitive, in caller order, no boxes
-            if (w.next != kEnd) {
-                w.prim = w.next | (__ldg(&sc.nodes[w.next].kind) << 31); w.need_gate = false;
-                w.next = w.next + 1 < sc.n_prims ? w.next + 1 : kEnd;
-            }
-        } else {
-            // ---- hot walk: f32-eligible lanes take up to two steps per vote -----------------------------------
-            for (;;) {
-#pragma unroll
-                for (int rep = 0; rep < 2; ++rep)
-                    if ((w.next != kEnd) & (w.prim == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
-                const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim == kNoPrim) & w.m32);
-                if (walking == 0u) break;
-                const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
-                if (__popc(parked) >= tune.prim_batch) break;
-                if (more && __popc(~(walking | parked)) >= tune.refill_min) break;
-            }
-            // ---- lanes outside the f32 path's preconditions take one exact step per round ------------------
-            if (__any_sync(0xffffffffu, !w.m32)) {
-                if ((w.next != kEnd) & (w.prim == kNoPrim) & !w.m32) walker_step64<COUNT>(w, sc, lc);
-            }
-        }
-
-        // ---- leaves: exact gate + primitive test for the parked lanes --------------------------------
-        if (w.prim != kNoPrim) walker_leaf<COUNT>(w, sc, lc);
-    }
-
-    flush_counters<COUNT>(counters, lc);
-    // the last block to drain rearms the queue, so back-to-back launches need no memset
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&wq->done_blocks, 1u) == gridDim.x - 1) {
-            wq->next = 0ull;
-            wq->done_blocks = 0u;
-            __threadfence();
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1133,6 +1042,182 @@ __global__ void __launch_bounds__(256) wave_shade_kernel(DSceneView sc, DRender 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The persistent traversal kernel (state and steps: Walker above). Defined here because its tail mode shades in place.
+// ---------------------------------------------------------------------------------------------
+
+// Tail mode (OUT_TAIL) of the wavefront integrator: when queue `bounce` holds at most `threshold` rays, one launch
+// carries every surviving path to its end. A lane whose ray is finished shades it in place (shade_vertex) and, if the
+// path scattered, restarts its walker on the scattered ray, so the remaining bounces cost one kernel instead of two
+// launches each, and the culling tree stays warm in L1 across them. Results are the same bits: per path the
+// sequence ray -> closest hit -> shade_vertex is the one the trace/shade kernels perform.
+struct TailArgs {
+    WaveQueues q;
+    DRender rp;
+    double4* scratch;
+    uint32_t bounce;
+    uint32_t threshold;
+};
+
+template <bool COUNT, int OUT, bool LIST>
+__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : 5) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+                                                                  Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev,
+                                                                  TailArgs ta) {
+    extern __shared__ uint32_t wide_stack[];  // [level][thread]
+    if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
+    if (OUT == OUT_TAIL) {
+        if (n == 0 || n > ta.threshold) return;  // the trace/shade pair that follows handles this queue
+        rays = ta.q.rays[ta.bounce & 1u];
+    }
+    uint4 pst = make_uint4(0, 0, 0, 0);  // tail mode: the path state of the lane's ray (WaveQueues::state)
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t* const my_stack = wide_stack + threadIdx.x;
+    const uint32_t stride = blockDim.x;
+    constexpr size_t kNoRay = ~static_cast<size_t>(0);
+    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+
+    // lane state: next == kEnd && prim == kNoPrim  -> empty (its finished ray, if any, is written at the next refill);
+    //             prim != kNoPrim                  -> parked at a leaf;  otherwise walking
+    Walker w;
+    w.o = w.d = w.inv = mk(0, 0, 0);
+    w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
+    w.next = kEnd; w.prim = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
+    w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
+    w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    size_t idx = kNoRay;
+    bool more = true;  // warp-uniform: the queue may still hold rays
+    const size_t n_warps = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
+    const int lane_cap = static_cast<int>(min(static_cast<size_t>(32), max(static_cast<size_t>(tune.min_lanes), (n + n_warps - 1) / n_warps)));
+    const int refill_thr = min(tune.refill_min, max(1, lane_cap / 2));
+
+    for (;;) {
+        // ---- retire finished rays and refill ----------------------------------------------------------
+        const bool is_done = (w.next == kEnd) & (w.prim == kNoPrim);
+        const bool fin = OUT == OUT_TAIL && is_done && idx != kNoRay;  // tail mode: walk over, vertex not shaded yet
+        const bool is_empty = is_done & !fin;
+        const unsigned empty = __ballot_sync(0xffffffffu, is_empty);
+        const int room = min(__popc(empty), max(lane_cap - (32 - __popc(empty)), 0));  // rays this warp may take now
+        if (OUT == OUT_TAIL) {
+            // shade finished rays in place; a path that scattered keeps its lane and walks on
+            const unsigned finished = __ballot_sync(0xffffffffu, fin);
+            if (finished != 0u && (__popc(finished) >= tune.prim_batch || __ballot_sync(0xffffffffu, !is_done) == 0u)) {
+                if (fin) {
+                    uint32_t depth = pst.z & 0xFFu, nb = (pst.z >> 8) & 0xFFu, first_hit = (pst.z >> 16) & 1u;
+                    const size_t p = pst.x;
+                    bool alive = false;
+                    D3 L = mk(0.0, 0.0, 0.0), o = w.o, d = w.d;
+                    if (w.h.slot == kNoPrim) {
+                        L = shade_miss(sc, d);
+                    } else {
+                        if (depth == ta.rp.max_bounce) first_hit = 1u;  // the path's first segment (render.rs:102-122)
+                        uint32_t pi, pj, smp;
+                        path_coords(ta.rp, p, pi, pj, smp);
+                        Rng rng;
+                        rng_init(rng, ta.rp.seed, pj * ta.rp.width + pi, smp, RTP_RNG_STREAM_PATH);
+                        rng.k = pst.y;
+                        D3 emit, absorb;
+                        if (!shade_vertex(sc, o, d, w.h, rng, emit, absorb)) {
+                            L = emit + mk(0.0, 0.0, 0.0);
+                        } else {
+                            double2* sp = ta.q.stack + (static_cast<size_t>(nb) * ta.q.capacity + p) * 3;
+                            sp[0] = make_double2(emit.x, emit.y);
+                            sp[1] = make_double2(emit.z, absorb.x);
+                            sp[2] = make_double2(absorb.y, absorb.z);
+                            ++nb;
+                            depth -= 1;
+                            pst.y = rng.k;
+                            if (depth != 0) alive = true;  // render.rs:128-131 otherwise
+                        }
+                    }
+                    pst.z = depth | (nb << 8) | (first_hit << 16);
+                    if (alive) {
+                        walker_start(w, sc, tune, o, d, kRayEpsilon, CUDART_INF);
+                        if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
+                        lc.rays++;
+                    } else {
+                        for (int b = static_cast<int>(nb) - 1; b >= 0; --b) {
+                            const double2* sp = ta.q.stack + (static_cast<size_t>(b) * ta.q.capacity + p) * 3;
+                            const double2 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+                            L = mk(s0.x, s0.y, s1.x) + cmul(mk(s1.y, s2.x, s2.y), L);
+                        }
+                        ta.scratch[p] = make_double4(L.x, L.y, L.z, first_hit ? 1.0 : 0.0);
+                        idx = kNoRay;
+                    }
+                }
+                continue;
+            }
+        }
+        if (empty == 0xffffffffu || (more && room >= refill_thr)) {
+            if (OUT != OUT_TAIL && is_empty && idx != kNoRay) {
+                write_hit<OUT>(sc, out, idx, w.o, w.d, w.h);
+                idx = kNoRay;
+            }
+            if (!more) break;  // every lane is empty and the queue is drained
+            // small batches are spread over all resident warps (fewer rays per warp, shorter critical path) instead of
+            // filling a few warps to 32 lanes: a warp never holds more than lane_cap rays
+            const int cnt = room, leader = __ffs(empty) - 1;
+            unsigned long long base = 0;
+            if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
+            if (is_empty) {
+                const int rank = __popc(empty & lt_mask);
+                const size_t i = static_cast<size_t>(base) + rank;
+                if (rank < cnt && i < n) {
+                    idx = i;
+                    const double2* rp = reinterpret_cast<const double2*>(rays + i);
+                    const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+                    walker_start(w, sc, tune, mk(r0.x, r0.y, r1.x), mk(r1.y, r2.x, r2.y), r3.x, r3.y);
+                    if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
+                    if (OUT == OUT_TAIL) pst = ta.q.state[ta.bounce & 1u][i];
+                    lc.rays++;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, w.next != kEnd) == 0u) continue;
+        }
+
+        if (LIST) {
+            // hittable.rs:110-120: every primitive, in caller order, no boxes
+            if (w.next != kEnd) {
+                w.prim = w.next | (__ldg(&sc.nodes[w.next].kind) << 31); w.need_gate = false;
+                w.next = w.next + 1 < sc.n_prims ? w.next + 1 : kEnd;
+            }
+        } else {
+            // ---- hot walk: f32-eligible lanes take up to two steps per vote -----------------------------------
+            for (;;) {
+                for (int rep = 0; rep < tune.walk_reps; ++rep)
+                    if ((w.next != kEnd) & (w.prim == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
+                const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim == kNoPrim) & w.m32);
+                if (walking == 0u) break;
+                const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
+                if (__popc(parked) >= tune.prim_batch) break;
+                if (more && min(__popc(~(walking | parked)), max(lane_cap - __popc(walking | parked), 0)) >= refill_thr) break;
+            }
+            // ---- lanes outside the f32 path's preconditions take one exact step per round ------------------
+            if (__any_sync(0xffffffffu, !w.m32)) {
+                if ((w.next != kEnd) & (w.prim == kNoPrim) & !w.m32) walker_step64<COUNT>(w, sc, lc);
+            }
+        }
+
+        // ---- leaves: exact gate + primitive test for the parked lanes --------------------------------
+        if (w.prim != kNoPrim) walker_leaf<COUNT>(w, sc, lc);
+    }
+
+    flush_counters<COUNT>(counters, lc);
+    // the last block to drain rearms the queue, so back-to-back launches need no memset
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&wq->done_blocks, 1u) == gridDim.x - 1) {
+            wq->next = 0ull;
+            wq->done_blocks = 0u;
+            if (OUT == OUT_TAIL) ta.q.count[ta.bounce] = 0ull;  // every path is finished: the launches that follow find empty queues
+            __threadfence();
+        }
+    }
+}
+
 // main.rs:78-87: per pixel, add the samples of this launch in sample order to the running sums; on the
 // last launch optionally divide by num_samples. acc is (r,g,b,foreground) per tile pixel.
 __global__ void __launch_bounds__(256) resolve_kernel(const double4* __restrict__ scratch, double4* __restrict__ acc, size_t npix, uint32_t n_samples,
@@ -1189,7 +1274,7 @@ struct DeviceScene {
     unsigned queue_seq = 0;
     int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
-    Tuning tune{16, 8, 1, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
+    Tuning tune{16, 8, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
@@ -1199,6 +1284,9 @@ struct DeviceScene {
     WaveQueues wave{};                 // wavefront integrator queues (render_device), grown on demand
     uint32_t wave_bounces = 0;         // stack depth the queues were sized for
     int shade_blocks = 0;              // grid of wave_shade_kernel
+    int tail_blocks = 0;               // grid of the tail-mode traversal kernel
+    uint32_t tail_threshold = 65536;   // RTP_TAIL_THRESHOLD: a launch this small is finished by one tail-mode launch (0 = never)
+    bool tail_offer = false;           // RTP_TAIL_OFFER
     bool use_simple_render = false;    // RTP_RENDER_KERNEL=simple
     double* frame = nullptr; size_t frame_elems = 0;
 };
@@ -1273,6 +1361,11 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, ds->stack_bytes);
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 4;
+        int tail_per_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false>, 128, ds->stack_bytes);
+        ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
+        if (const char* v = std::getenv("RTP_TAIL_THRESHOLD")) ds->tail_threshold = static_cast<uint32_t>(std::max(0l, std::atol(v)));
+        if (const char* v = std::getenv("RTP_TAIL_OFFER")) ds->tail_offer = std::atoi(v) != 0;
         const char* env = std::getenv("RTP_TRACE_KERNEL");
         ds->use_simple_kernel = env && std::string(env) == "simple";
         env = std::getenv("RTP_RENDER_KERNEL");
@@ -1281,6 +1374,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         if (const char* v = std::getenv("RTP_PRIM_BATCH")) ds->tune.prim_batch = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
         if (const char* v = std::getenv("RTP_F32_CULLING")) ds->tune.f32_culling = std::atoi(v) != 0;
+        if (const char* v = std::getenv("RTP_MIN_LANES")) ds->tune.min_lanes = std::max(1, std::min(32, std::atoi(v)));
+        if (const char* v = std::getenv("RTP_WALK_REPS")) ds->tune.walk_reps = std::max(1, std::min(16, std::atoi(v)));
         if (!flat.boxes_finite) ds->tune.fast_slab = 0;
     }
     for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
@@ -1312,7 +1407,7 @@ static DCamera make_camera(const rtp_camera* c) {
 // One traversal launch. out_mode: OUT_HIT / OUT_FULL / OUT_WAVE. n_dev != nullptr: the batch size is read from device memory
 // (wavefront integrator) and `n` is only an upper bound used to size the grid.
 static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* d_out, int out_mode, bool count, Counters* counters,
-                        cudaStream_t stream, const unsigned long long* n_dev = nullptr) {
+                        cudaStream_t stream, const unsigned long long* n_dev = nullptr, const TailArgs* tail = nullptr) {
     if (n == 0) return RTP_OK;
     const unsigned block = 128;
     if (ds->use_simple_kernel && !n_dev && out_mode != OUT_WAVE) {
@@ -1327,12 +1422,13 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
             else trace_closest_kernel<false, false><<<g, block, 0, stream>>>(ds->view, d_rays, n, d_out, counters);
         }
     } else {
-        // persistent grid: a whole number of resident blocks per SM, never more blocks than there are warps of work
-        const size_t want = (n + block - 1) / block;
-        const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->persistent_blocks), want)));
+        // persistent grid: a whole number of resident blocks per SM, never more warps than rays
+        const size_t want = (n + 3) / 4;  // a warp per ray at least: small batches are latency-bound per warp, so they are spread thin
+        const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(out_mode == OUT_TAIL ? ds->tail_blocks : ds->persistent_blocks), want)));
         WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
-#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev)
+        const TailArgs ta = tail ? *tail : TailArgs{};
+#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta)
 #define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
     do {                                                                                             \
         if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true); else RTP_LAUNCH_PERSISTENT(false, O, true); }     \
@@ -1340,6 +1436,7 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
     } while (0)
         if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
         else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);
+        else if (out_mode == OUT_TAIL) RTP_LAUNCH_PERSISTENT_O(OUT_TAIL);
         else RTP_LAUNCH_PERSISTENT_O(OUT_HIT);
 #undef RTP_LAUNCH_PERSISTENT_O
 #undef RTP_LAUNCH_PERSISTENT
@@ -1481,7 +1578,19 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
             ++launches;
             const unsigned shade_grid = static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->shade_blocks), (total + 255) / 256));
             for (uint32_t b = 0; b < p->max_bounce; ++b) {
-                int rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, ds->wave.count + b);
+                int rc;
+                // a launch of at most tail_threshold paths (a 32x32 tile of main.rs:32, say) runs as generate + ONE tail-mode launch.
+                // RTP_TAIL_OFFER=1 also offers every later queue of a big launch to the tail kernel, which declines the ones above
+                // the threshold; measured on C1 it is no faster than trace/shade pairs (both are bound by per-ray latency), so off.
+                const bool tail_certain = total <= ds->tail_threshold;
+                if (ds->tail_threshold && (tail_certain || (ds->tail_offer && b > 0))) {
+                    TailArgs ta{ds->wave, rp, ds->scratch, b, ds->tail_threshold};
+                    rc = launch_trace(ds, ds->wave.rays[b & 1], total, nullptr, OUT_TAIL, count, ds->counters, st, ds->wave.count + b, &ta);
+                    if (rc != RTP_OK) return rc;
+                    ++launches;
+                    if (tail_certain) break;
+                }
+                rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, ds->wave.count + b);
                 if (rc != RTP_OK) return rc;
                 wave_shade_kernel<<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch);
                 RTP_CUDA(cudaGetLastError());

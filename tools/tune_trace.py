@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--c3-log2", type=int, default=22)
     ap.add_argument("--grid", default="refill=4,8,12,16;prim=4,8,12,16;fast=1")
     ap.add_argument("--scene", default="bunny_lambert")
+    ap.add_argument("--reps", default="2")
     args = ap.parse_args()
     grid = dict(kv.split("=") for kv in args.grid.split(";"))
     api.init(0)
@@ -46,11 +47,13 @@ def main():
     h2 = torch.empty((c2.shape[0], 2), dtype=torch.float64, device="cuda")
     h3 = torch.empty((c3.shape[0], 2), dtype=torch.float64, device="cuda")
     ref2 = ref3 = None
-    print(f"{'kernel':>8} {'refill':>6} {'prim':>5} {'fast':>4} {'C2 Mrays/s':>11} {'C3 Mrays/s':>11}")
-    combos = [("simple", 0, 0, 0)] + [("persist", int(r), int(p), int(f)) for r, p, f in
-                                      itertools.product(grid["refill"].split(","), grid["prim"].split(","), grid["fast"].split(","))]
+    print(f"{'kernel':>8} {'refill':>6} {'prim':>5} {'reps':>4} {'C2 Mrays/s':>11} {'C3 Mrays/s':>11}")
+    combos = [("persist", int(r), int(p), int(f)) for r, p, f in
+              itertools.product(grid["refill"].split(","), grid["prim"].split(","), args.reps.split(","))]
     for kern, r, p, f in combos:
         os.environ["RTP_TRACE_KERNEL"] = kern
+        os.environ["RTP_WALK_REPS"] = str(f)
+        f = 1
         os.environ["RTP_REFILL_MIN"], os.environ["RTP_PRIM_BATCH"], os.environ["RTP_FAST_SLAB"] = str(r or 8), str(p or 8), str(f)
         scene = api.Scene(sc)
         m2 = time_batch(scene, c2, h2)
@@ -59,7 +62,7 @@ def main():
         if ref2 is None:
             ref2, ref3 = a2, a3
         ok = bool((a2.view(torch.int64) == ref2.view(torch.int64)).all() and (a3.view(torch.int64) == ref3.view(torch.int64)).all())
-        print(f"{kern:>8} {r:>6} {p:>5} {f:>4} {m2:>11.1f} {m3:>11.1f} {'' if ok else 'MISMATCH'}", flush=True)
+        print(f"{kern:>8} {r:>6} {p:>5} {os.environ['RTP_WALK_REPS']:>4} {m2:>11.1f} {m3:>11.1f} {'' if ok else 'MISMATCH'}", flush=True)
         scene.close()
 
 
