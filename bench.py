@@ -148,11 +148,13 @@ def main():
         run_reference(args)
         return
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("RTP_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
     import torch
     import torch.distributed as dist
 
     from rtp_b200 import _abi as A
     from rtp_b200 import api, scenes
+    from rtp_b200 import dist as rdist
 
     rank, local_rank, world = dist_env()
     if world != args.gpus and world > 1:
@@ -241,6 +243,29 @@ def main():
     # --- roofline inputs: work counters of one counted pass (outside any timed region) ---------------------------------
     cst = scene.hit_device_counted(d_rays[0].data_ptr(), N_RAYS, d_hits.data_ptr())
 
+    # --- secondary: C3 incoherent batch (2^22 of the 2^24 rays per rank; secondary-ray divergence stress) ----------------------
+    incoherent = None
+    if not args.no_render:
+        n3 = 1 << 22
+        d3 = torch.from_numpy(scenes.incoherent_rays(n3, first=rank * n3).view(np.float64).reshape(-1, 8)).to(dev)
+        h3 = torch.empty((n3, 2), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            scene.hit_device(d3.data_ptr(), n3, h3.data_ptr(), stream)
+        barrier()
+        e0.record()
+        reps3 = max(3, min(args.steps, 20))
+        for _ in range(reps3):
+            scene.hit_device(d3.data_ptr(), n3, h3.data_ptr(), stream)
+        e1.record()
+        barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        c3 = scene.hit_device_counted(d3.data_ptr(), n3, h3.data_ptr())
+        incoherent = {"workload": "C3 subset: 2^22 incoherent rays per GPU vs bunny BVH (268 MB of rays > L2)", "mrays_per_s": reps3 * n3 * world / (float(ms3.item()) * 1e-3) / 1e6,
+                      "per_ray": {"node_visits": c3.node_visits / n3, "leaf_gates": c3.leaf_gates / n3, "triangle_tests": c3.triangle_tests / n3, "sphere_tests": c3.sphere_tests / n3}}
+        del d3, h3
+
     # --- secondary: C1 render (640x360, 16 spp per rank, depth 8), sample ranges + NCCL sum -----------------------------
     render = None
     if not args.no_render:
@@ -261,15 +286,15 @@ def main():
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("trace_closest_kernel_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("trace_persistent_kernel_c2_dram_bytes_per_launch")
     except Exception:
         pass
     clocks = sampler.report()
     sm_hz = (clocks["sm_mhz"] or 1965) * 1e6
     # f64 work of the reference algorithm per launch: 24 ops per slab test, 75 per triangle test, 20 per sphere test
-    f64_ops = 24 * cst.node_visits + 75 * cst.triangle_tests + 20 * cst.sphere_tests
+    f64_ops = 24 * cst.leaf_gates + 75 * cst.triangle_tests + 20 * cst.sphere_tests  # inner nodes are culled in f32
     fp64_peak = 148 * 64 * sm_hz  # 64 FP64 lanes per SM
-    scene_bytes = 64 * cst.node_visits + 80 * (cst.triangle_tests + cst.sphere_tests)
+    scene_bytes = 128 * cst.node_visits + 128 * cst.leaf_gates  # one 128 B DWide per node visit, one 128 B DPrim per leaf
 
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -285,17 +310,21 @@ def main():
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": {
-            "kernel": "trace_closest_kernel<false,false>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "kernel": "trace_persistent_kernel<COUNT=false, OUT_HIT, LIST=false>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms,
-            "note": "the bunny scene (1.7 MB) is L2-resident, so HBM carries only the 80 B/ray stream; the kernel is bound by FP64 issue and L2 latency, see fp64/l2 below",
+            "note": "the bunny scene (0.9 MB of culling nodes + primitives) is cache-resident, so HBM carries only the 80 B/ray stream; the kernel is bound by instruction issue and L1 latency (profiles/): see issue/fp64 below",
             "fp64": {"ops_per_launch": f64_ops, "achieved_gops": f64_ops / (kernel_ms * 1e-3) / 1e9, "peak_gops": fp64_peak / 1e9,
                      "frac": f64_ops / (kernel_ms * 1e-3) / fp64_peak, "peak_source": "148 SM x 64 FP64 lanes x median SM clock during the run"},
             "l2": {"bytes_per_launch": scene_bytes, "achieved_gbs": scene_bytes / (kernel_ms * 1e-3) / 1e9},
-            "per_ray": {"node_visits": cst.node_visits / N_RAYS, "triangle_tests": cst.triangle_tests / N_RAYS, "sphere_tests": cst.sphere_tests / N_RAYS},
+            "l1_note": "scene bytes are served by L1/L2, not HBM",
+            "per_ray": {"node_visits": cst.node_visits / N_RAYS, "leaf_gates": cst.leaf_gates / N_RAYS, "triangle_tests": cst.triangle_tests / N_RAYS, "sphere_tests": cst.sphere_tests / N_RAYS,
+                        "conservative_violations": int(cst.conservative_violations)},
         },
     }
     if render is not None:
         line["render"] = render
+    if incoherent is not None:
+        line["incoherent"] = incoherent
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(sc, cam)
     print(json.dumps(line), flush=True)
@@ -337,7 +366,10 @@ def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream,
     spp = spp_rank * world
     cam = api.Camera(rw / rh, sc.camera.fov, sc.camera.focal_dist, sc.camera.lens_radius, sc.camera.transformation)
     acc = torch.zeros((rh * rw * 4,), dtype=torch.float64, device=dev)  # rgb (3*npix) then foreground (npix)
-    p = api.render_params(rw, rh, spp, depth, seed=1, sample_begin=rank * spp_rank, sample_end=(rank + 1) * spp_rank, flags=A.RENDER_RAW_SUMS)
+    from rtp_b200 import dist as rdist
+
+    sb, se = rdist.sample_range(spp, rank, world)
+    p = api.render_params(rw, rh, spp, depth, seed=1, sample_begin=sb, sample_end=se, flags=A.RENDER_RAW_SUMS)
     st = scene.render_device(p, cam, acc.data_ptr(), acc.data_ptr() + rh * rw * 3 * 8, stream, stats=True)
     rays_rank = torch.tensor([float(st.rays)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -350,8 +382,7 @@ def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream,
     e0.record()
     for _ in range(steps):
         scene.render_device(p, cam, acc.data_ptr(), acc.data_ptr() + rh * rw * 3 * 8, stream)
-        if world > 1:
-            dist.all_reduce(acc)
+        rdist.reduce_frame(acc)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -7,7 +7,7 @@ provides their inputs. The directory name contains a hyphen; import it with
 `importlib.import_module("raytracing-potato_b200")` (see `rtp_b200.py` at the repo root).
 """
 from . import _abi  # noqa: F401
-from . import api, assets, scenes  # noqa: F401
+from . import api, assets, dist, scenes  # noqa: F401
 from .api import *  # noqa: F401,F403
 
-__all__ = ["api", "assets", "scenes", "_abi"]
+__all__ = ["api", "assets", "dist", "scenes", "_abi"]
