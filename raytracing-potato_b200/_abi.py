@@ -190,7 +190,8 @@ PROTOTYPES = {
     "rtp_rng_draws": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "librtp_b200.so")
+# RTP_B200_LIB: another build of the same library (kernel A/B runs from tools/); it is still this product's CUDA library
+LIB_PATH = os.environ.get("RTP_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "librtp_b200.so")
 _lib = None
 
 

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const
 
 struct WorkQueue {
     unsigned long long next;   // next unclaimed ray index
-    unsigned int done_blocks;  // blocks that have drained; the last one resets the queue for the next launch
+    unsigned int done_blocks;  // warps that have drained; the last one resets the queue for the next launch
     unsigned int _pad;
 };
 
@@ -1059,8 +1059,10 @@ struct TailArgs {
     uint32_t threshold;
 };
 
+constexpr int kTraceBlocksPerSM = 6;
+
 template <bool COUNT, int OUT, bool LIST>
-__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : 5) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev,
                                                                   TailArgs ta) {
     extern __shared__ uint32_t wide_stack[];  // [level][thread]
@@ -1205,11 +1207,11 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : 5) trace_persistent
     }
 
     flush_counters<COUNT>(counters, lc);
-    // the last block to drain rearms the queue, so back-to-back launches need no memset
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    // the last warp to drain rearms the queue, so back-to-back launches need no memset (no block barrier: warps leave
+    // as soon as they are done)
+    if (lane == 0) {
         __threadfence();
-        if (atomicAdd(&wq->done_blocks, 1u) == gridDim.x - 1) {
+        if (atomicAdd(&wq->done_blocks, 1u) == static_cast<unsigned>(n_warps) - 1u) {
             wq->next = 0ull;
             wq->done_blocks = 0u;
             if (OUT == OUT_TAIL) ta.q.count[ta.bounce] = 0ull;  // every path is finished: the launches that follow find empty queues
