@@ -291,14 +291,24 @@ __device__ __forceinline__ void finish_triangle(const DSceneView& sc, const HitR
     s.v = (w * u0.y + h.u * u1.y) + h.v * u2.y;
 }
 
-__device__ __forceinline__ void finish_sphere(const DSceneView& sc, const HitRec& h, Surface& s) {
+__device__ __forceinline__ void finish_sphere(const DSceneView& sc, const HitRec& h, Surface& s, bool want_uv = true) {
     const DPrim* p = sc.prims + h.slot;
     const double* pd = reinterpret_cast<const double*>(p);
     const double2 q0 = ldg2(pd), q1 = ldg2(pd + 2);
     const D3 center = mk(q0.x, q0.y, q1.x);
     s.normal = normalize(s.position - center);  // hittable.rs:60
-    s.u = 0.5 - atan2(s.normal.z, s.normal.x) / kTau;  // hittable.rs:61
-    s.v = asin(s.normal.y) / kPi + 0.5;
+    if (want_uv) {
+        s.u = 0.5 - atan2(s.normal.z, s.normal.x) / kTau;  // hittable.rs:61
+        s.v = asin(s.normal.y) / kPi + 0.5;
+    } else {
+        s.u = 0.0; s.v = 0.0;  // never read: see material_reads_uv
+    }
+}
+
+// Hit::uv (hittable.rs:61) is only consumed by Texture::sample (texture.rs:21-36), i.e. by an AlbedoMap absorb or a
+// SkySphere emit of the hit material; the two f64 transcendentals of the sphere uv are skipped for every other material.
+__device__ __forceinline__ bool material_reads_uv(const DMaterial* m) {
+    return __ldg(&m->absorb) == RTP_ABSORB_ALBEDO_MAP || __ldg(&m->emit_kind) == RTP_EMIT_SKY_SPHERE;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -540,10 +550,14 @@ template <bool COUNT>
 __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, LocalCounters& lc) {
     const uint32_t slot = w.prim & 0x7FFFFFFFu, kind = w.prim >> 31;
     const DPrim* p = sc.prims + slot;
+    // bvh.rs:96-97 accepts a leaf iff its slab gate AND its primitive test pass; both are pure functions of (ray, t_max,
+    // leaf), so the order of evaluation is free. The gate passes for ~94% of the leaves the f32 walk hands out, so the
+    // primitive goes first and the exact gate only confirms an accepted hit. The counting kernels keep the reference's
+    // order, so their test counters are the oracle's.
     bool open = true;
-    if (w.need_gate) {
+    if (COUNT && w.need_gate) {
         const double* pb = p->bmin;
-        if (COUNT) lc.leaf_gates++;
+        lc.leaf_gates++;
         open = collide_fast(ldg2(pb), ldg2(pb + 2), ldg2(pb + 4), w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, w.h.t);
     }
     if (open) {
@@ -555,6 +569,10 @@ __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, Loc
         } else {
             if (COUNT) lc.sphere_tests++;
             hit = test_sphere(p, w.o, w.d, w.tmin, w.h.t, t);
+        }
+        if (!COUNT && hit && w.need_gate) {
+            const double* pb = p->bmin;
+            hit = collide_fast(ldg2(pb), ldg2(pb + 2), ldg2(pb + 4), w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, w.h.t);
         }
         if (hit) {  // bvh.rs:107-111: shrink t_max, later hit replaces
             w.h.t = t; w.h.u = u; w.h.v = v; w.h.slot = slot; w.h.kind = kind;
@@ -825,9 +843,9 @@ __device__ __forceinline__ D3 shade_miss(const DSceneView& sc, D3 d) {
 __device__ __forceinline__ bool shade_vertex(const DSceneView& sc, D3& o, D3& d, const HitRec& h, Rng& rng, D3& emit, D3& absorb) {
     Surface s;
     finish_hit(sc, o, d, h, s);
-    if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
-    else finish_sphere(sc, h, s);
     const DMaterial* m = sc.materials + s.material;
+    if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
+    else finish_sphere(sc, h, s, material_reads_uv(m));
 
     // material.rs:104-110: scatter, then absorb, then emit
     bool scattered = false;
@@ -1188,7 +1206,8 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
         } else {
             // ---- hot walk: f32-eligible lanes take up to two steps per vote -----------------------------------
             for (;;) {
-                for (int rep = 0; rep < tune.walk_reps; ++rep)
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep)
                     if ((w.next != kEnd) & (w.prim == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
                 const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim == kNoPrim) & w.m32);
                 if (walking == 0u) break;
