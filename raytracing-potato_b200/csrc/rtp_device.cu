@@ -700,8 +700,9 @@ __device__ __forceinline__ D3 sample_unit_sphere(Rng& r) {
 // ---------------------------------------------------------------------------------------------
 
 // Rust `as u32` / `as isize`: saturating, NaN -> 0
-__device__ __forceinline__ uint32_t sat_u32(double x) { return __double2uint_rz(x); }  // cvt.rzi.u32.f64 saturates, NaN -> 0
-__device__ __forceinline__ long long sat_i64(double x) { return __double2ll_rz(x); }   // cvt.rzi.s64.f64 saturates, NaN -> 0
+// cvt.rzi saturates like Rust, but maps NaN to 0x80000000 / INT64_MIN where Rust's `as` gives 0
+__device__ __forceinline__ uint32_t sat_u32(double x) { return x != x ? 0u : __double2uint_rz(x); }
+__device__ __forceinline__ long long sat_i64(double x) { return x != x ? 0ll : __double2ll_rz(x); }
 // f64::clamp: NaN stays NaN
 __device__ __forceinline__ double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
@@ -739,6 +740,9 @@ __device__ D3 texture_sample(const DSceneView& sc, uint32_t tid, D3 position, do
                 const double w = static_cast<double>(wi), h = static_cast<double>(hi);
                 const uint32_t i = sat_u32(clampd(hu * w, 0.0, w - 1.0));
                 const uint32_t j = sat_u32(clampd(hv * h, 0.0, h - 1.0));
+#ifdef RTP_DEVICE_CHECKS
+                if (i >= wi || j >= hi || tid >= 64) printf("texture_sample: tid %u i %u j %u of %u x %u (hu %g hv %g)\n", tid, i, j, wi, hi, hu, hv);
+#endif
                 const uchar4* texels = reinterpret_cast<const uchar4*>(tx->rgba);
                 const uchar4 px = __ldg(texels + (static_cast<size_t>(i) + static_cast<size_t>(j) * wi));  // image.rs:31-33
                 return mk(static_cast<double>(px.x) / 255.0, static_cast<double>(px.y) / 255.0, static_cast<double>(px.z) / 255.0);
@@ -842,7 +846,13 @@ __device__ __forceinline__ D3 shade_miss(const DSceneView& sc, D3 d) {
 // render.rs:105-115 for a hit: returns true when the material scattered (then o, d hold the scattered ray, render.rs:111-114).
 __device__ __forceinline__ bool shade_vertex(const DSceneView& sc, D3& o, D3& d, const HitRec& h, Rng& rng, D3& emit, D3& absorb) {
     Surface s;
+#ifdef RTP_DEVICE_CHECKS
+    if (h.slot >= sc.n_prims) printf("shade_vertex: slot %u of %u kind %u t %g\n", h.slot, sc.n_prims, h.kind, h.t);
+#endif
     finish_hit(sc, o, d, h, s);
+#ifdef RTP_DEVICE_CHECKS
+    if (s.material >= 64) printf("shade_vertex: material %u slot %u\n", s.material, h.slot);
+#endif
     const DMaterial* m = sc.materials + s.material;
     if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
     else finish_sphere(sc, h, s, material_reads_uv(m));
@@ -1309,6 +1319,7 @@ struct DeviceScene {
     uint32_t tail_threshold = 65536;   // RTP_TAIL_THRESHOLD: a launch this small is finished by one tail-mode launch (0 = never)
     bool tail_offer = false;           // RTP_TAIL_OFFER
     bool use_simple_render = false;    // RTP_RENDER_KERNEL=simple
+    bool debug_sync = false;           // RTP_DEBUG_SYNC
     double* frame = nullptr; size_t frame_elems = 0;
 };
 
@@ -1391,6 +1402,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         ds->use_simple_kernel = env && std::string(env) == "simple";
         env = std::getenv("RTP_RENDER_KERNEL");
         ds->use_simple_render = env && std::string(env) == "simple";
+        env = std::getenv("RTP_DEBUG_SYNC");
+        ds->debug_sync = env && std::atoi(env) != 0;
         if (const char* v = std::getenv("RTP_REFILL_MIN")) ds->tune.refill_min = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_PRIM_BATCH")) ds->tune.prim_batch = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
@@ -1427,6 +1440,14 @@ static DCamera make_camera(const rtp_camera* c) {
 
 // One traversal launch. out_mode: OUT_HIT / OUT_FULL / OUT_WAVE. n_dev != nullptr: the batch size is read from device memory
 // (wavefront integrator) and `n` is only an upper bound used to size the grid.
+// RTP_DEBUG_SYNC=1: synchronise after every launch of the integrator and name the kernel that faulted
+static int debug_sync(const DeviceScene* ds, cudaStream_t st, const char* what, uint32_t bounce) {
+    if (!ds->debug_sync) return RTP_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return set_error(RTP_ERR_CUDA, std::string(what) + " (segment " + std::to_string(bounce) + "): " + cudaGetErrorString(e));
+    return RTP_OK;
+}
+
 static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* d_out, int out_mode, bool count, Counters* counters,
                         cudaStream_t stream, const unsigned long long* n_dev = nullptr, const TailArgs* tail = nullptr) {
     if (n == 0) return RTP_OK;
@@ -1597,6 +1618,7 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
             wave_generate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(cam, rp, ds->wave, total);
             RTP_CUDA(cudaGetLastError());
             ++launches;
+            { int rc = debug_sync(ds, st, "wave_generate_kernel", 0); if (rc != RTP_OK) return rc; }
             const unsigned shade_grid = static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->shade_blocks), (total + 255) / 256));
             for (uint32_t b = 0; b < p->max_bounce; ++b) {
                 int rc;
@@ -1613,8 +1635,10 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
                 }
                 rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, ds->wave.count + b);
                 if (rc != RTP_OK) return rc;
+                if ((rc = debug_sync(ds, st, "trace_persistent_kernel<OUT_WAVE>", b)) != RTP_OK) return rc;
                 wave_shade_kernel<<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch);
                 RTP_CUDA(cudaGetLastError());
+                if ((rc = debug_sync(ds, st, "wave_shade_kernel", b)) != RTP_OK) return rc;
                 launches += 2;
             }
         } else {

@@ -304,3 +304,110 @@ def test_errors_are_reported_not_thrown(gpu):
     with pytest.raises(api.RtpError) as e:
         g.render(16, 16, 1, max_bounce=0)  # assert!(depth >= 1), render.rs:97
     assert e.value.code == A.ERR_INVALID
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE sizes, through size-independent properties (the oracle finishes only subsets of these in seconds)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _device_hits(g, d_rays):
+    import torch
+
+    d_hits = torch.empty((d_rays.shape[0], 2), dtype=torch.float64, device="cuda")
+    g.hit_device(d_rays.data_ptr(), d_rays.shape[0], d_hits.data_ptr())
+    torch.cuda.synchronize()
+    return d_hits
+
+
+def test_c3_full_16m_rays_two_algorithms_agree(gpu, monkeypatch):
+    """BASELINE config C3 at full size: all 2^24 incoherent rays. The production kernel (4-wide f32-culled walk, persistent
+    warps) and the exact f64 pre-order walk of the reference topology in the one-thread-per-ray kernel are different
+    algorithms over different trees; they must agree bit for bit on every ray, and with the oracle on every 1021st ray."""
+    import torch
+
+    sc = scenes.bunny_lambert()
+    g = api.Scene(sc)
+    monkeypatch.setenv("RTP_TRACE_KERNEL", "simple")
+    monkeypatch.setenv("RTP_TREE", "reference")
+    ge = api.Scene(sc)
+    monkeypatch.delenv("RTP_TRACE_KERNEL"); monkeypatch.delenv("RTP_TREE")
+    o = oracle.Scene(sc)
+    n, chunk = 1 << 24, 1 << 22
+    kinds = np.zeros(3, dtype=np.int64)
+    for first in range(0, n, chunk):
+        rays = scenes.incoherent_rays(chunk, first=first)
+        d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+        a, b = _device_hits(g, d_rays), _device_hits(ge, d_rays)
+        assert bool((a.view(torch.int64) == b.view(torch.int64)).all()), first
+        hg = a.cpu().numpy().view(A.HIT_DTYPE).reshape(-1)
+        sub = slice(first % 1021, chunk, 1021)
+        assert_hits_equal_bits(hg[sub], o.hit(rays[sub]))
+        kinds += [int((hg["leaf"] < 4968).sum()), int((hg["leaf"] == 4968).sum()), int((hg["leaf"] == A.MISS).sum())]
+    frac = kinds / n
+    assert 0.30 < frac[0] < 0.42 and 0.50 < frac[1] < 0.64 and 0.03 < frac[2] < 0.12, frac  # SURVEY.md §8d: ~36 / 57 / 8 %
+    g.close(); ge.close(); o.close()
+
+
+def test_c4_full_resolution_frame_properties(gpu):
+    """BASELINE config C4 geometry at 1920x1080 (1 of its 256 spp): tiling is only a work partition (main.rs:36), so 32x32
+    tiles stitched through the tail-mode path equal the whole-frame wavefront render bit for bit; a sample-range split
+    reproduces the frame up to f64 re-association; and the oracle agrees on a 96x54 crop rendered as its own tile."""
+    sc = scenes.demo()
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    w, h = 1920, 1080
+    full, ffg, st = g.render(w, h, 2, seed=5)
+    assert st.paths == w * h * 2 and st.rays >= st.paths
+    stitched = np.zeros_like(full)
+    for (oi, oj, tw, th) in api.split_in_tiles(w, h, 256, 256):
+        g.render(w, h, 2, seed=5, tile=(int(oi), int(oj), int(tw), int(th)), out=stitched)
+    assert stitched.tobytes() == full.tobytes()
+    a, _, _ = g.render(w, h, 2, seed=5, sample_range=(0, 1), flags=A.RENDER_RAW_SUMS)
+    b, _, _ = g.render(w, h, 2, seed=5, sample_range=(1, 2), flags=A.RENDER_RAW_SUMS)
+    assert np.allclose((a + b) / 2, full, rtol=1e-14, atol=1e-15)
+    tile = (900, 500, 96, 54)
+    ref = np.zeros_like(full)
+    o_img, _, _ = o.render(w, h, 2, seed=5, tile=tile)
+    crop = (slice(tile[1], tile[1] + tile[3]), slice(tile[0], tile[0] + tile[2]))
+    rep = image_report(full[crop], o_img[crop])
+    assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+    g.close(); o.close()
+
+
+def test_c5_reduced_bunny_field_matches_oracle(gpu):
+    """BASELINE config C5 scene generator at 8x4 copies (158,977 leaves): closest hits and a small render vs the oracle. The full
+    64x32 field (10.2 M triangles, 5 GiB) is exercised by tools/c5_run.py, which checks the f32-culled walk against the exact walk."""
+    sc = scenes.bunny_field(8, 4)
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    assert g.info().n_leaves == o.info().n_leaves == 8 * 4 * 4968 + 1
+    assert (g.leaf_order() == o.leaf_order()).all()
+    cam = api.Camera(16 / 9, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+    rays = oracle.camera_rays(cam, 640, 360)
+    rng = np.random.default_rng(3)
+    shuffled = rays.copy()
+    shuffled["direction"] = rays["direction"][rng.permutation(len(rays))]
+    both = np.concatenate([rays, shuffled])
+    assert_hits_equal_bits(g.hit(both), o.hit(both))
+    ig, fg, sg = g.render(160, 90, 2, seed=2)
+    io, fo, so = o.render(160, 90, 2, seed=2)
+    rep = image_report(ig, io)
+    assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+    g.close(); o.close()
+
+
+def test_nan_uv_samples_texel_row_zero_like_rust(gpu):
+    """`Hit::at_infinity` takes asin(dir.y) of a NON-unit direction (utility.rs:93-100; the camera basis is scaled by |up x z|,
+    utility.rs:174). With a long `up` vector dir.y exceeds 1, asin is NaN, f64::clamp keeps NaN and `NaN as u32` is 0
+    (texture.rs:40-49): those pixels read texel row 0. CUDA's cvt maps NaN to 0x80000000 instead — regression for that."""
+    from rtp_b200.api import Camera, Transformation
+
+    sc = scenes.bunny_lambert()
+    sc.camera = Camera(1.0, sc.camera.fov, 1.0, 0.0, Transformation.lookat([0.0, 0.3, 2.0], [0.0, 2.5, 0.0], [0.0, 3.0, 0.0]))
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    cam = api.Camera(1.0, sc.camera.fov, 1.0, 0.0, sc.camera.transformation)
+    rays = oracle.camera_rays(cam, 64, 64)
+    assert (np.abs(rays["direction"][:, 1]) > 1.0).any()  # the premise: asin gets arguments outside [-1, 1]
+    ig, fg, _ = g.render(64, 64, 2, seed=4)
+    io, fo, _ = o.render(64, 64, 2, seed=4)
+    rep = image_report(ig, io)
+    assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+    g.close(); o.close()
