@@ -300,6 +300,12 @@ int rtp_trace_closest(rtp_scene* scene, const rtp_ray* rays, size_t n, rtp_hit* 
 /* Same, plus the interpolated `Hit` fields (hittable.rs:58-62, 102-107). */
 int rtp_trace_closest_full(rtp_scene* scene, const rtp_ray* rays, size_t n, rtp_hit_full* hits_out,
                            rtp_stats* stats);
+/* main.rs:67-77 without the jitter: for every pixel of a width x height frame (i fastest, row j = 0 at the bottom),
+ * `Camera::shoot` at the pixel centre u=(i+0.5)/W, v=(j+0.5)/H with lens_radius treated as 0 (render.rs:32-52), then
+ * `Hittable::hit` on the scene root. The reference never materialises a ray array — the camera is the input of this
+ * path — so rays are produced on the device and only the hits travel back to the host buffer. */
+int rtp_trace_camera(rtp_scene* scene, const rtp_camera* camera, uint32_t width, uint32_t height, rtp_hit* hits_out,
+                     rtp_stats* stats);
 /* Same for rays/results already resident in device memory. `cuda_stream` is a cudaStream_t
  * (NULL = the legacy default stream); the call is asynchronous with respect to the host. */
 int rtp_trace_closest_device(rtp_scene* scene, const rtp_ray* d_rays, size_t n, rtp_hit* d_hits_out,

@@ -523,6 +523,14 @@ class Scene:
         _check(self._lib, self._lib.rtp_trace_closest(self._h, A.ptr(rays), len(rays), A.ptr(hits), C.byref(st) if stats else None))
         return (hits, st) if stats else hits
 
+    def hit_camera(self, camera: Camera, width: int, height: int, out: Optional[np.ndarray] = None, stats: bool = False):
+        """main.rs:67-77 at pixel centres: Camera::shoot + Hittable::hit per pixel, rays generated on the device (rtp_trace_camera)"""
+        hits = out if out is not None else np.empty(width * height, dtype=A.HIT_DTYPE)
+        st = A.Stats()
+        cc = camera.to_c()
+        _check(self._lib, self._lib.rtp_trace_camera(self._h, C.byref(cc), width, height, A.ptr(hits), C.byref(st) if stats else None))
+        return (hits, st) if stats else hits
+
     def hit_full(self, rays: np.ndarray) -> np.ndarray:
         rays = _as_rays(rays)
         hits = np.empty(len(rays), dtype=A.HIT_FULL_DTYPE)

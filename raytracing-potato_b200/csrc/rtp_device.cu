@@ -609,10 +609,12 @@ __device__ __forceinline__ void camera_shoot(const DCamera& cam, double u, doubl
            ((m[2] * origin.x + m[5] * origin.y) + m[8] * origin.z) + cam.pos[2]);
 }
 
-__global__ void __launch_bounds__(256) camera_rays_kernel(DCamera cam, uint32_t width, uint32_t height, rtp_ray* __restrict__ rays) {
-    const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t n = static_cast<size_t>(width) * height;
-    if (p >= n) return;
+// writes the rays of pixels [first, first + count) (i fastest) to rays[0 .. count)
+__global__ void __launch_bounds__(256) camera_rays_kernel(DCamera cam, uint32_t width, uint32_t height, rtp_ray* __restrict__ rays_out, size_t first, size_t count) {
+    const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    const size_t p = first + q;
+    rtp_ray* rays = rays_out - first;
     const uint32_t i = static_cast<uint32_t>(p % width), j = static_cast<uint32_t>(p / width);
     const double u = (static_cast<double>(i) + 0.5) / static_cast<double>(width);
     const double v = (static_cast<double>(j) + 0.5) / static_cast<double>(height);
@@ -1488,7 +1490,9 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
 }
 
 // Host-buffer batch: chunks flow H2D → kernel → D2H on kPipeDepth streams so copies overlap traversal.
-static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hits_out, bool full, rtp_stats* stats) {
+// `camera` != nullptr: the rays are pixel-centre camera rays generated on the device chunk by chunk (rtp_trace_camera)
+static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hits_out, bool full, rtp_stats* stats, const DCamera* camera = nullptr,
+                      uint32_t width = 0, uint32_t height = 0) {
     DeviceScene* ds = scene->dev;
     std::lock_guard<std::mutex> guard(ds->lock);
     RTP_CUDA(cudaSetDevice(ds->device));
@@ -1506,7 +1510,13 @@ static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hit
         const size_t m = std::min(kChunkRays, n - off);
         const int k = static_cast<int>(chunk_id % kPipeDepth);
         cudaStream_t st = ds->streams[k];
-        RTP_CUDA(cudaMemcpyAsync(ds->stage_rays[k], rays + off, m * sizeof(rtp_ray), cudaMemcpyHostToDevice, st));
+        if (camera) {
+            camera_rays_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(*camera, width, height, ds->stage_rays[k], off, m);
+            RTP_CUDA(cudaGetLastError());
+            ++launches;
+        } else {
+            RTP_CUDA(cudaMemcpyAsync(ds->stage_rays[k], rays + off, m * sizeof(rtp_ray), cudaMemcpyHostToDevice, st));
+        }
         int rc = launch_trace(ds, ds->stage_rays[k], m, ds->stage_hits[k], full ? OUT_FULL : OUT_HIT, false, count ? ds->counters : nullptr, st);
         if (rc != RTP_OK) return rc;
         ++launches;
@@ -1797,6 +1807,15 @@ int rtp_trace_closest_full(rtp_scene* scene, const rtp_ray* rays, size_t n, rtp_
     return trace_host(scene, rays, n, hits_out, true, stats);
 }
 
+int rtp_trace_camera(rtp_scene* scene, const rtp_camera* camera, uint32_t width, uint32_t height, rtp_hit* hits_out, rtp_stats* stats) {
+    if (!scene || !camera || !hits_out) return set_error(RTP_ERR_INVALID, "null argument");
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const size_t n = static_cast<size_t>(width) * height;
+    if (n == 0) return RTP_OK;
+    const DCamera cam = make_camera(camera);
+    return trace_host(scene, nullptr, n, hits_out, false, stats, &cam, width, height);
+}
+
 int rtp_trace_closest_device(rtp_scene* scene, const rtp_ray* d_rays, size_t n, rtp_hit* d_hits_out, void* cuda_stream) {
     if (!scene || (n && (!d_rays || !d_hits_out))) return set_error(RTP_ERR_INVALID, "null argument");
     RTP_CUDA(cudaSetDevice(scene->dev->device));
@@ -1833,7 +1852,7 @@ int rtp_camera_rays_device(const rtp_camera* camera, uint32_t width, uint32_t he
     const size_t n = static_cast<size_t>(width) * height;
     if (n == 0) return RTP_OK;
     const DCamera cam = make_camera(camera);
-    camera_rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(cam, width, height, d_rays_out);
+    camera_rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(cam, width, height, d_rays_out, 0, n);
     RTP_CUDA(cudaGetLastError());
     return RTP_OK;
 }

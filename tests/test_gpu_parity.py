@@ -69,6 +69,16 @@ def test_c2_primary_batch_bit_exact(bunny_pair):
     assert 0.15 < frac < 0.19
 
 
+def test_trace_camera_equals_ray_batch(bunny_pair):
+    """rtp_trace_camera (rays generated on the device from the camera, only hits return) == rtp_trace_closest on the same
+    pixel-centre rays == the oracle; odd sizes exercise the chunk boundaries of the copy pipeline"""
+    sc, g, o = bunny_pair
+    for (w, h) in ((1920, 1080), (1000, 333), (7, 3)):
+        cam = primary(sc, w, h)
+        hc = g.hit_camera(cam, w, h)
+        assert_hits_equal(hc, o.hit(oracle.camera_rays(cam, w, h)), f"camera {w}x{h}")
+
+
 def test_c3_incoherent_subset_bit_exact(bunny_pair):
     """BASELINE config C3 (first 2^20 rays of the 2^24 stream)"""
     sc, g, o = bunny_pair
