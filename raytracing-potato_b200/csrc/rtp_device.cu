@@ -858,6 +858,9 @@ __device__ __forceinline__ bool shade_vertex(const DSceneView& sc, D3& o, D3& d,
     const DMaterial* m = sc.materials + s.material;
     if (h.kind == RTP_HITTABLE_TRIANGLE) finish_triangle(sc, h, s);
     else finish_sphere(sc, h, s, material_reads_uv(m));
+    // every scattering material draws at least once: generate the block of the next draw here, where all lanes of the warp
+    // are still together, instead of inside the per-material branches (the stream itself is unchanged)
+    if (__ldg(&m->scatter) != RTP_SCATTER_NONE) philox_block(rng, rng.k >> 1);
 
     // material.rs:104-110: scatter, then absorb, then emit
     bool scattered = false;
@@ -993,7 +996,7 @@ __global__ void __launch_bounds__(256) wave_generate_kernel(DCamera cam, DRender
     wq.state[0][p] = make_uint4(static_cast<uint32_t>(p), rng.k, rp.max_bounce, 0u);
 }
 
-__global__ void __launch_bounds__(256) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch) {
+__global__ void __launch_bounds__(256, 3) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch) {
     const size_t n = static_cast<size_t>(wq.count[bounce]);
     const int cur = bounce & 1, nxt = cur ^ 1;
     const unsigned lane = threadIdx.x & 31u;
@@ -1394,7 +1397,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         int per_sm = 0;
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, ds->stack_bytes);
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
-        ds->shade_blocks = prop.multiProcessorCount * 4;
+        ds->shade_blocks = prop.multiProcessorCount * 3;
         int tail_per_sm = 0;
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false>, 128, ds->stack_bytes);
         ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
