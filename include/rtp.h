@@ -204,6 +204,7 @@ typedef struct rtp_render_params {
 
 #define RTP_RENDER_RAW_SUMS 1u /* write Σ over the sample range instead of Σ / num_samples   */
 #define RTP_RENDER_COUNTERS 2u /* also count node visits / primitive tests (slower kernel)   */
+#define RTP_RENDER_TRANSPARENT 4u /* rtp_render_srgb8: alpha = (255 * foreground) as u8 (main.rs:111,116-118) */
 
 typedef struct rtp_stats {
     uint64_t rays;          /* closest-hit queries (`scene.hit` calls, render.rs:105,133)  */
@@ -333,6 +334,12 @@ int rtp_camera_rays(const rtp_camera* camera, uint32_t width, uint32_t height, r
  * tile rectangle are written. Host buffers. */
 int rtp_render(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params,
                double* rgb_out, double* foreground_out, rtp_stats* stats);
+/* rtp_render followed by the output stage of main.rs:110-122 on the device: per pixel `to_srgb_u8` (utility.rs:212-220) of
+ * the averaged colour, alpha 255 or, with RTP_RENDER_TRANSPARENT, `(255 * foreground) as u8` (main.rs:116-118). rgba_out is
+ * width*height*4 bytes, pixel (i,j) at 4*(i + j*width), ready for rtp_tga_save; only the tile rectangle is written.
+ * The bytes equal rtp_frame_to_srgb8 of rtp_render's frame (borderline pixels are redone with the host libm). */
+int rtp_render_srgb8(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, uint8_t* rgba_out,
+                     rtp_stats* stats);
 /* Same with device output buffers; asynchronous on `cuda_stream` except for stats (pass NULL
  * stats to avoid the synchronisation). */
 int rtp_render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params,

@@ -23,7 +23,7 @@ ABSORB_BLACKBODY, ABSORB_WHITEBODY, ABSORB_ALBEDO, ABSORB_ALBEDO_MAP = 0, 1, 2, 
 EMIT_NONE, EMIT_DEBUG_NORMALS, EMIT_COLOR, EMIT_SKY_GRADIENT, EMIT_SKY_SPHERE = 0, 1, 2, 3, 4
 TEXTURE_MISSING, TEXTURE_DEBUG_UVS, TEXTURE_SOLID, TEXTURE_IMAGE, TEXTURE_CHECKER, TEXTURE_NOISE, TEXTURE_PERLIN = range(7)
 ROOT_BVH, ROOT_LIST = 0, 1
-RENDER_RAW_SUMS, RENDER_COUNTERS = 1, 2
+RENDER_RAW_SUMS, RENDER_COUNTERS, RENDER_TRANSPARENT = 1, 2, 4
 RNG_STREAM_PATH, RNG_STREAM_RAYS = 0, 1
 
 # numpy views of the POD records that travel in bulk
@@ -187,6 +187,7 @@ PROTOTYPES = {
     "rtp_camera_rays": (C.c_int, [_P(Camera), C.c_uint32, C.c_uint32, C.c_void_p]),
     "rtp_render": (C.c_int, [C.c_void_p, _P(Camera), _P(RenderParams), C.c_void_p, C.c_void_p, _P(Stats)]),
     "rtp_render_device": (C.c_int, [C.c_void_p, _P(Camera), _P(RenderParams), C.c_void_p, C.c_void_p, _P(Stats), C.c_void_p]),
+    "rtp_render_srgb8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtp_trace_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rtp_rng_draws": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
 }

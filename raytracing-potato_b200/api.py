@@ -559,6 +559,18 @@ class Scene:
         _check(self._lib, self._lib.rtp_render(self._h, C.byref(cc), C.byref(p), A.ptr(rgbf), A.ptr(fg) if fg is not None else None, C.byref(st)))
         return rgbf, fg, st
 
+    def render_srgb8(self, width: int, height: int, num_samples: int, max_bounce: int = 8, seed: int = 1, camera: Optional[Camera] = None,
+                     tile=None, transparent_background: bool = False, out: Optional[np.ndarray] = None):
+        """main.rs:61-122: render + tile merge + to_srgb_u8 with the output stage on the device; [height, width, 4] uint8, ready for tga.save"""
+        cam = camera or self.camera
+        cam = Camera(width / height, cam.fov, cam.focal_dist, cam.lens_radius, cam.transformation)
+        p = render_params(width, height, num_samples, max_bounce, seed, 0, None, tile, A.RENDER_TRANSPARENT if transparent_background else 0)
+        rgba = out if out is not None else np.zeros((height, width, 4), dtype=np.uint8)
+        st = A.Stats()
+        cc = cam.to_c()
+        _check(self._lib, self._lib.rtp_render_srgb8(self._h, C.byref(cc), C.byref(p), A.ptr(rgba), C.byref(st)))
+        return rgba, st
+
     def render_device(self, params: A.RenderParams, camera: Camera, d_rgb: int, d_fg: int = 0, stream: int = 0, stats: bool = False):
         st = A.Stats()
         cc = camera.to_c()

@@ -1282,6 +1282,47 @@ __global__ void __launch_bounds__(256) write_frame_kernel(const double4* __restr
     if (fg) fg[px] = a.w;
 }
 
+// Output stage (main.rs:110-122 + utility.rs:212-220 to_srgb_u8): colour = sum / divisor, clamp, gamma 1/2.2, `as u8`;
+// alpha = 255, or (255 * foreground) as u8 with RTP_RENDER_TRANSPARENT. CUDA's pow and the host libm's powf may differ in
+// the last ulps, which matters only when 255 * x^(1/2.2) lands within 1e-9 of an integer: those pixels (a handful per
+// frame at most) are appended to a fix-up list with their f64 colour and redone by the host with its own libm, so the
+// bytes are the reference's.
+struct SrgbFix {
+    uint32_t pixel, _pad;
+    double rgb[3];
+};
+
+__device__ __forceinline__ uint8_t sat_u8(double y) { return y != y || y <= 0.0 ? 0 : (y >= 255.0 ? 255 : static_cast<uint8_t>(static_cast<int>(y))); }
+
+__global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ acc, DRender rp, double divisor, int transparent, uchar4* __restrict__ rgba,
+                                                     SrgbFix* __restrict__ fixes, unsigned int* __restrict__ n_fixes, unsigned int fix_cap) {
+    const size_t npix = static_cast<size_t>(rp.tile_w) * rp.tile_h;
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const uint32_t i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
+    const uint32_t j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+    const size_t px = static_cast<size_t>(i) + static_cast<size_t>(j) * rp.width;
+    double4 a = acc[pix];
+    if (divisor != 0.0) { a.x = a.x / divisor; a.y = a.y / divisor; a.z = a.z / divisor; a.w = a.w / divisor; }
+    const double c[3] = {a.x, a.y, a.z};
+    uint8_t out[3];
+    bool ambiguous = false;
+    for (int k = 0; k < 3; ++k) {
+        const double x = clampd(c[k], 0.0, 1.0);
+        const double y = 255.0 * pow(x, 1.0 / 2.2);
+        out[k] = sat_u8(y);
+        if (x > 0.0 && x < 1.0 && fabs(y - rint(y)) < 1e-9) ambiguous = true;
+    }
+    rgba[px] = make_uchar4(out[0], out[1], out[2], transparent ? sat_u8(255.0 * a.w) : 0xff);
+    if (ambiguous) {
+        const unsigned int slot = atomicAdd(n_fixes, 1u);
+        if (slot < fix_cap) {
+            fixes[slot].pixel = static_cast<uint32_t>(px);
+            fixes[slot].rgb[0] = c[0]; fixes[slot].rgb[1] = c[1]; fixes[slot].rgb[2] = c[2];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // device scene
 // ---------------------------------------------------------------------------------------------
@@ -1326,6 +1367,8 @@ struct DeviceScene {
     bool use_simple_render = false;    // RTP_RENDER_KERNEL=simple
     bool debug_sync = false;           // RTP_DEBUG_SYNC
     double* frame = nullptr; size_t frame_elems = 0;
+    uchar4* frame8 = nullptr; size_t frame8_elems = 0;  // RGBA8 output stage
+    SrgbFix* fixes = nullptr; unsigned int* n_fixes = nullptr;
 };
 
 template <class T>
@@ -1349,7 +1392,7 @@ void device_scene_free(DeviceScene* ds) {
     }
     if (ds->ev_begin) cudaEventDestroy(ds->ev_begin);
     if (ds->ev_end) cudaEventDestroy(ds->ev_end);
-    cudaFree(ds->scratch); cudaFree(ds->acc); cudaFree(ds->frame);
+    cudaFree(ds->scratch); cudaFree(ds->acc); cudaFree(ds->frame); cudaFree(ds->frame8); cudaFree(ds->fixes); cudaFree(ds->n_fixes);
     cudaFree(ds->wave.rays[0]); cudaFree(ds->wave.rays[1]); cudaFree(ds->wave.state[0]); cudaFree(ds->wave.state[1]);
     cudaFree(ds->wave.hits); cudaFree(ds->wave.stack); cudaFree(ds->wave.count);
     delete ds;
@@ -1575,8 +1618,11 @@ static int wave_reserve(DeviceScene* ds, size_t capacity, uint32_t bounces) {
     return RTP_OK;
 }
 
+constexpr unsigned int kSrgbFixCap = 1u << 16;
+
+// d_rgba8 != nullptr: the output stage runs on the device (srgb8_kernel) instead of write_frame_kernel
 static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* p, double* d_rgb, double* d_fg, rtp_stats* stats,
-                         cudaStream_t st) {
+                         cudaStream_t st, uchar4* d_rgba8 = nullptr) {
     DeviceScene* ds = scene->dev;
     if (p->max_bounce < 1) return set_error(RTP_ERR_INVALID, "assert!(depth >= 1) (render.rs:97)");
     if (p->max_bounce > 128) return set_error(RTP_ERR_UNSUPPORTED, "max_bounce > 128");
@@ -1667,7 +1713,13 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
         first = false;
     }
     const double divisor = (p->flags & RTP_RENDER_RAW_SUMS) ? 0.0 : static_cast<double>(p->num_samples);
-    write_frame_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, st>>>(ds->acc, rp, divisor, d_rgb, d_fg);
+    if (d_rgba8) {
+        RTP_CUDA(cudaMemsetAsync(ds->n_fixes, 0, sizeof(unsigned int), st));
+        srgb8_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, st>>>(ds->acc, rp, divisor, (p->flags & RTP_RENDER_TRANSPARENT) ? 1 : 0, d_rgba8,
+                                                                                ds->fixes, ds->n_fixes, kSrgbFixCap);
+    } else {
+        write_frame_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, st>>>(ds->acc, rp, divisor, d_rgb, d_fg);
+    }
     RTP_CUDA(cudaGetLastError());
     ++launches;
     if (stats) {
@@ -1883,6 +1935,47 @@ int rtp_render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_rend
     std::lock_guard<std::mutex> guard(ds->lock);
     RTP_CUDA(cudaSetDevice(ds->device));
     return render_device(scene, camera, params, d_rgb_out, d_foreground_out, stats, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int rtp_render_srgb8(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, uint8_t* rgba_out, rtp_stats* stats) {
+    if (!scene || !camera || !params || !rgba_out) return set_error(RTP_ERR_INVALID, "null argument");
+    if (params->flags & RTP_RENDER_RAW_SUMS) return set_error(RTP_ERR_INVALID, "RTP_RENDER_RAW_SUMS has no 8-bit output");
+    DeviceScene* ds = scene->dev;
+    std::lock_guard<std::mutex> guard(ds->lock);
+    RTP_CUDA(cudaSetDevice(ds->device));
+    const size_t npx = static_cast<size_t>(params->width) * params->height;
+    if (npx == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
+    if (ds->frame8_elems < npx) {
+        cudaFree(ds->frame8); ds->frame8 = nullptr; ds->frame8_elems = 0;
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->frame8), npx * sizeof(uchar4)));
+        ds->frame8_elems = npx;
+    }
+    if (!ds->fixes) {
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->fixes), kSrgbFixCap * sizeof(SrgbFix)));
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->n_fixes), sizeof(unsigned int)));
+    }
+    cudaStream_t st = ds->streams[0];
+    int rc = render_device(scene, camera, params, nullptr, nullptr, stats, st, ds->frame8);
+    if (rc != RTP_OK) return rc;
+    const uint32_t W = params->width, tx = params->tile_x, ty = params->tile_y;
+    const uint32_t tw = params->tile_w ? params->tile_w : W - tx, th = params->tile_h ? params->tile_h : params->height - ty;
+    const size_t first = static_cast<size_t>(tx) + static_cast<size_t>(ty) * W;
+    RTP_CUDA(cudaMemcpy2DAsync(rgba_out + 4 * first, static_cast<size_t>(W) * 4, ds->frame8 + first, static_cast<size_t>(W) * 4, static_cast<size_t>(tw) * 4, th,
+                               cudaMemcpyDeviceToHost, st));
+    unsigned int n_fix = 0;
+    RTP_CUDA(cudaMemcpyAsync(&n_fix, ds->n_fixes, sizeof n_fix, cudaMemcpyDeviceToHost, st));
+    RTP_CUDA(cudaStreamSynchronize(st));
+    if (n_fix > kSrgbFixCap) return set_error(RTP_ERR_UNSUPPORTED, "more than 65536 pixels need the host libm fix-up; use rtp_render + rtp_frame_to_srgb8");
+    if (n_fix) {  // redo the borderline pixels with the host libm (utility.rs:213 powf as the reference's target evaluates it)
+        std::vector<SrgbFix> fixes(n_fix);
+        RTP_CUDA(cudaMemcpy(fixes.data(), ds->fixes, n_fix * sizeof(SrgbFix), cudaMemcpyDeviceToHost));
+        for (const SrgbFix& f : fixes) {
+            uint8_t px[4];
+            rtp_frame_to_srgb8(f.rgb, 1, 1, px);
+            std::memcpy(rgba_out + 4 * static_cast<size_t>(f.pixel), px, 3);
+        }
+    }
+    return RTP_OK;
 }
 
 int rtp_render(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, double* rgb_out, double* foreground_out,

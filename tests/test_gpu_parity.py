@@ -421,3 +421,29 @@ def test_nan_uv_samples_texel_row_zero_like_rust(gpu):
     rep = image_report(ig, io)
     assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
     g.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["bunny_lambert", "demo", "one_triangle"])
+def test_output_stage_on_device(gpu, name):
+    """main.rs:110-122 on the device (rtp_render_srgb8): the RGBA8 frame equals to_srgb_u8 of the f64 frame byte for byte —
+    against this library's own f64 frame and against the oracle's (where the oracle's frame is bit-identical); the transparent
+    background variant writes alpha = (255 * foreground) as u8; tiles stitch."""
+    sc = getattr(scenes, name)()
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    w, h, spp = 240, 135, 3
+    frame, fg, _ = g.render(w, h, spp, seed=6)
+    rgba, st = g.render_srgb8(w, h, spp, seed=6)
+    assert rgba.tobytes() == api.to_srgb_u8(frame).tobytes()
+    assert st.paths == w * h * spp
+    io, fo, _ = o.render(w, h, spp, seed=6)
+    same = (io == frame).all(axis=-1)
+    assert same.mean() > 0.999
+    assert (rgba[same] == oracle.to_srgb_u8(io)[same]).all()
+    ta, _ = g.render_srgb8(w, h, spp, seed=6, transparent_background=True)
+    assert (ta[..., :3] == rgba[..., :3]).all()
+    assert (ta[..., 3] == np.minimum(255.0 * fg, 255.0).astype(np.uint8)).all()
+    stitched = np.zeros_like(rgba)
+    for (oi, oj, tw, th) in api.split_in_tiles(w, h, 64, 64):
+        g.render_srgb8(w, h, spp, seed=6, tile=(int(oi), int(oj), int(tw), int(th)), out=stitched)
+    assert stitched.tobytes() == rgba.tobytes()
+    g.close(); o.close()
