@@ -1789,7 +1789,8 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
     *out = nullptr;
     try {
         rtp_scene* s = new rtp_scene();
-        int rc = flatten_scene(desc, &s->flat);
+        int rc = require_device();
+        if (rc == RTP_OK) rc = flatten_scene(desc, &s->flat, /*device_build=*/true);
         if (rc == RTP_OK) rc = device_scene_upload(s->flat, &s->dev);
         if (rc != RTP_OK) { delete s; return rc; }
         s->n_leaves = static_cast<uint32_t>(s->flat.prims.size());

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +49,7 @@ struct Builder {
     std::vector<BuildItem>& items;
     std::vector<DNode>& nodes;
     std::atomic<uint32_t> depth{0};
+    bool presorted = false;  // `items` are already in DFS-rank order (device_reference_order): build boxes only
 
     // bvh.rs:36-56 make_bvh + bvh.rs:58-67 split, writing nodes straight into pre-order position.
     // A range of n leaves occupies 2n-1 consecutive nodes starting at `base`; the left half
@@ -68,7 +70,7 @@ struct Builder {
             nd.kind = 0;  // filled by the caller once primitives are laid out
             return;
         }
-        std::sort(items.begin() + lo, items.begin() + lo + n, [axis](const BuildItem& x, const BuildItem& y) {
+        if (!presorted) std::sort(items.begin() + lo, items.begin() + lo + n, [axis](const BuildItem& x, const BuildItem& y) {
             double kx = 0.5 * (x.bmin[axis] + x.bmax[axis]);
             double ky = 0.5 * (y.bmin[axis] + y.bmax[axis]);
             if (kx != ky) return kx < ky;
@@ -280,7 +282,7 @@ static bool emit_ok(const rtp_emit& e, uint32_t n_textures) {
     return e.kind != RTP_EMIT_SKY_SPHERE || e.texture < n_textures;
 }
 
-int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
+int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     if (!d || !out) return set_error(RTP_ERR_INVALID, "null scene description");
     if (d->abi_version != RTP_ABI_VERSION) return set_error(RTP_ERR_INVALID, "rtp_scene_desc.abi_version mismatch");
     if (d->root_kind > RTP_ROOT_LIST) return set_error(RTP_ERR_INVALID, "unknown root kind");
@@ -290,6 +292,15 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
     if (d->root_kind == RTP_ROOT_BVH && d->n_hittables == 0)
         return set_error(RTP_ERR_INVALID, "Bvh::new on an empty list is unreachable!() in the reference (bvh.rs:40)");
     if (d->n_hittables >= 0x3FFFFFFFu) return set_error(RTP_ERR_INVALID, "too many hittables");
+
+    const bool timing = std::getenv("RTP_BUILD_TIMING") != nullptr;  // phase times of the host build on stderr
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rtp build] %s: %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
 
     // ---- tables -------------------------------------------------------------------------
     out->root_kind = d->root_kind;
@@ -373,8 +384,26 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
     out->depth = 0;
     if (d->root_kind == RTP_ROOT_BVH) {
         out->nodes.assign(static_cast<size_t>(2) * n - 1, DNode{});
+        lap("tables, validation, leaf boxes");
         Builder b{items, out->nodes};
+        const char* dev_env = std::getenv("RTP_DEVICE_BUILD");  // "0": never, "1": always, unset: scenes of >= 65,536 leaves
+        const bool on_device = device_build && (dev_env ? std::atoi(dev_env) != 0 : n >= 65536u);
+        if (on_device) {
+            // bvh.rs:36-67 on the GPU: one segmented sort of all leaves per depth (rtp_build.cu), then the boxes bottom-up here
+            std::vector<double> boxes(static_cast<size_t>(n) * 6);
+            for (uint32_t i = 0; i < n; ++i)
+                for (int k = 0; k < 3; ++k) { boxes[6 * static_cast<size_t>(i) + k] = items[i].bmin[k]; boxes[6 * static_cast<size_t>(i) + 3 + k] = items[i].bmax[k]; }
+            std::vector<uint32_t> order(n);
+            int rc = device_reference_order(boxes.data(), n, order.data());
+            if (rc != RTP_OK) return rc;
+            std::vector<BuildItem> sorted(n);
+            for (uint32_t r = 0; r < n; ++r) sorted[r] = items[order[r]];
+            items.swap(sorted);
+            b.presorted = true;
+            lap("reference order on the device (segmented radix sorts)");
+        }
         b.build(0, n, 0, 0, 1, 4);  // sorts `items` into the reference's DFS-rank order
+        lap("reference median-split order (Bvh::new)");
         out->depth = b.depth.load();
         out->n_reference_nodes = static_cast<uint32_t>(out->nodes.size());
         const char* tree = std::getenv("RTP_TREE");  // "reference" keeps the median-split topology on the device (A/B runs, counter parity)
@@ -382,6 +411,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
             SeqBuilder sb{items, out->nodes};
             sb.build(0, n, 0, 1, 4);
             out->device_depth = sb.depth.load();
+            lap("SAH culling tree over the rank order");
         } else {
             out->device_depth = out->depth;
         }
@@ -433,10 +463,12 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out) {
             p.material = m.material;  // hittable.rs:107
         }
     }
+    lap("primitive and attribute records");
     if (d->root_kind == RTP_ROOT_BVH) {
         for (DNode& nd : out->nodes)
             if (nd.prim != kNoPrim) nd.kind = d->hittables[items[nd.prim].id].kind;
         build_wide(out);
+        lap("4-wide collapse");
     } else {
         // a List root is traversed as a flat run of leaves without slab tests; nodes carry only the kind
         out->nodes.assign(n ? n : 1, DNode{});

@@ -135,10 +135,12 @@ struct FlatScene {
 int set_error(int code, const std::string& msg);
 
 // host layer
-int flatten_scene(const rtp_scene_desc* desc, FlatScene* out);
+// device_build: compute the reference leaf order on the GPU (rtp_build.cu) when the scene is large; host-only callers pass false
+int flatten_scene(const rtp_scene_desc* desc, FlatScene* out, bool device_build = false);
 
-// device layer (rtp_device.cu)
+// device layer (rtp_device.cu, rtp_build.cu)
 struct DeviceScene;
+int device_reference_order(const double* boxes /* n x {min xyz, max xyz} */, uint32_t n, uint32_t* order_out /* item index by DFS rank */);
 int device_scene_upload(const FlatScene& flat, DeviceScene** out);
 void device_scene_free(DeviceScene* ds);
 uint64_t device_scene_bytes(const DeviceScene* ds);

@@ -447,3 +447,38 @@ def test_output_stage_on_device(gpu, name):
         g.render_srgb8(w, h, spp, seed=6, tile=(int(oi), int(oj), int(tw), int(th)), out=stitched)
     assert stitched.tobytes() == rgba.tobytes()
     g.close(); o.close()
+
+
+@pytest.mark.parametrize("name", ["bunny_lambert", "demo", "field", "ties"])
+def test_device_bvh_order_equals_reference_order(gpu, monkeypatch, name):
+    """§8f: `Bvh::new`'s depth-first leaf order computed on the GPU (rtp_build.cu: one segmented radix sort per depth) equals the
+    host build and the oracle leaf for leaf, including scenes where thousands of median splits straddle equal centroid keys
+    (ties go to the smaller LeafId) and keys of -0.0 / +0.0."""
+    if name == "field":
+        sc = scenes.bunny_field(8, 4)
+    elif name == "ties":
+        # a 24x24x3 lattice of identical small triangles (every centroid key repeats many times) plus mirrored copies
+        # whose keys are -0.0 and +0.0 on one axis
+        pos, idx = [], []
+        for k, (x, y, z) in enumerate((x, y, z) for x in range(-12, 12) for y in range(-12, 12) for z in (-1, 0, 1)):
+            base = len(pos)
+            pos += [[x, y, float(z)], [x + 0.5, y, float(z)], [x, y + 0.5, float(z)]]
+            idx += [base, base + 1, base + 2]
+        pos += [[-1.0, 0.0, 5.0], [1.0, 0.0, 5.0], [0.0, 0.0, 6.0], [1.0, -0.0, 5.0], [-1.0, -0.0, 5.0], [0.0, -0.0, 6.0]]
+        idx += [len(pos) - 6, len(pos) - 5, len(pos) - 4, len(pos) - 3, len(pos) - 2, len(pos) - 1]
+        mesh = api.Mesh.from_arrays(pos, indices=idx, material=0)
+        sc = scenes.one_triangle()
+        sc.scene_data.mesh_table[:] = [mesh]
+        sc.hittables = api.Hittable.triangles_of(mesh, 0)
+    else:
+        sc = getattr(scenes, name)()
+    monkeypatch.setenv("RTP_DEVICE_BUILD", "1")
+    g = api.Scene(sc)
+    monkeypatch.setenv("RTP_DEVICE_BUILD", "0")
+    gh = api.Scene(sc)
+    o = oracle.Scene(sc)
+    assert (g.leaf_order() == o.leaf_order()).all() and (gh.leaf_order() == o.leaf_order()).all()
+    cam = api.Camera(1.0, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+    rays = oracle.camera_rays(cam, 96, 96)
+    assert_hits_equal_bits(g.hit(rays), o.hit(rays))
+    g.close(); gh.close(); o.close()
