@@ -77,6 +77,7 @@ int device_reference_order(const double* boxes, uint32_t n, uint32_t* order_out)
         cudaFree(d_k64[0]); cudaFree(d_k64[1]); cudaFree(d_temp);
     };
     if (n == 0) return RTP_OK;
+    if (int rc = ensure_device()) return rc;
     RTP_CUDA_B(cudaMalloc(reinterpret_cast<void**>(&d_boxes), static_cast<size_t>(n) * 6 * sizeof(double)));
     RTP_CUDA_B(cudaMemcpy(d_boxes, boxes, static_cast<size_t>(n) * 6 * sizeof(double), cudaMemcpyHostToDevice));
     for (int k = 0; k < 2; ++k) {

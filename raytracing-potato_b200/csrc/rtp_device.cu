@@ -1407,6 +1407,8 @@ static int require_device() {
     return rtp_init(0);
 }
 
+int ensure_device() { return require_device(); }
+
 int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     int rc = require_device();
     if (rc != RTP_OK) return rc;
@@ -1789,8 +1791,7 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
     *out = nullptr;
     try {
         rtp_scene* s = new rtp_scene();
-        int rc = require_device();
-        if (rc == RTP_OK) rc = flatten_scene(desc, &s->flat, /*device_build=*/true);
+        int rc = flatten_scene(desc, &s->flat, /*device_build=*/true);  // validates before it touches the device
         if (rc == RTP_OK) rc = device_scene_upload(s->flat, &s->dev);
         if (rc != RTP_OK) { delete s; return rc; }
         s->n_leaves = static_cast<uint32_t>(s->flat.prims.size());

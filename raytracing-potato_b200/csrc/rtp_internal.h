@@ -140,6 +140,7 @@ int flatten_scene(const rtp_scene_desc* desc, FlatScene* out, bool device_build 
 
 // device layer (rtp_device.cu, rtp_build.cu)
 struct DeviceScene;
+int ensure_device();  // binds device 0 if rtp_init has not been called; RTP_ERR_CUDA without a usable sm_100 GPU
 int device_reference_order(const double* boxes /* n x {min xyz, max xyz} */, uint32_t n, uint32_t* order_out /* item index by DFS rank */);
 int device_scene_upload(const FlatScene& flat, DeviceScene** out);
 void device_scene_free(DeviceScene* ds);
