@@ -11,6 +11,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1348,7 +1349,7 @@ struct DeviceScene {
     std::mutex lock;  // serialises calls that use the scratch below
     Counters* counters = nullptr;
     WorkQueue* queues = nullptr;       // kQueueSlots self-rearming work queues, handed out round-robin per launch
-    unsigned queue_seq = 0;
+    std::atomic<unsigned> queue_seq{0};  // launches from several host threads never share a slot unless > kQueueSlots are in flight
     int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
     Tuning tune{16, 8, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
@@ -1517,7 +1518,7 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         // persistent grid: a whole number of resident blocks per SM, never more warps than rays
         const size_t want = (n + 3) / 4;  // a warp per ray at least: small batches are latency-bound per warp, so they are spread thin
         const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(out_mode == OUT_TAIL ? ds->tail_blocks : ds->persistent_blocks), want)));
-        WorkQueue* wq = ds->queues + (ds->queue_seq++ % kQueueSlots);
+        WorkQueue* wq = ds->queues + (ds->queue_seq.fetch_add(1u) % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
         const TailArgs ta = tail ? *tail : TailArgs{};
 #define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta)
