@@ -111,13 +111,6 @@ __device__ __forceinline__ bool collide_fast(const double2 b0, const double2 b1,
     return p0 & p1 & p2 & p3;
 }
 
-// out-of-line literal test for the rare rays that are not eligible for collide_fast (keeps the hot loop small)
-__device__ __noinline__ bool collide_literal_slow(const DNode* __restrict__ node, double ox, double oy, double oz, double ix, double iy, double iz,
-                                                  double tmin, double T) {
-    const double* nb = node->bmin;
-    return collide_literal(ldg2(nb), ldg2(nb + 2), ldg2(nb + 4), mk(ox, oy, oz), mk(ix, iy, iz), tmin, T);
-}
-
 // Conservative f32 culling. Inputs: a child's outward-inflated f32 box (rtp_internal.h DWide), inv32 = RN32(1/d), and per
 // axis c_lo = RD32(-(o*inv) - K), c_hi = RU32(-(o*inv) + K) with K = 2^-21 |o*inv| + 1e-37. Then
 //   n_lo = fma(near_plane, inv32, c_lo) <= the f64 slab entry (min-o)*inv as the reference rounds it, and
@@ -452,7 +445,9 @@ struct Walker {
     uint32_t cur, pend, sp;
     uint32_t c0, c1, c2, c3;
     uint32_t onx, ony, onz;  // byte offset of the near plane inside each axis block of a DWide (0 or 16)
-    uint32_t prim;   // kNoPrim, or slot | kind << 31 of the leaf the lane is parked at
+    uint32_t prim;   // kNoPrim, or slot | kind << 31 of the oldest leaf handed out and not tested yet
+    uint32_t prim2;  // f32 walk only: a second pending leaf. The lane keeps walking (with a stale, larger t_max: conservative)
+                     // until two leaves are pending; they are tested strictly in the order they were handed out
     bool fast;       // eligible for collide_fast (finite, non-axis-parallel, no NaN)
     bool m32;        // eligible for the f32 culling walk
     bool need_gate;  // parked by the f32 walk: the leaf's exact f64 gate has not been evaluated yet
@@ -482,7 +477,7 @@ __device__ __forceinline__ void walker_start(Walker& w, const DSceneView& sc, co
     }
     w.next = 0;
     w.pend = 0; w.sp = 0; w.cur = 0;
-    w.prim = kNoPrim;
+    w.prim = kNoPrim; w.prim2 = kNoPrim;
     w.need_gate = false;
 }
 
@@ -525,7 +520,8 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
     w.pend &= w.pend - 1u;
     const uint32_t c = k == 0u ? w.c0 : (k == 1u ? w.c1 : (k == 2u ? w.c2 : w.c3));
     if (c & kWideLeaf) {
-        w.prim = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+        const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+        if (w.prim == kNoPrim) w.prim = leaf; else w.prim2 = leaf;
         w.need_gate = true;
     } else {
         if (w.pend) { stack[w.sp * stride] = (w.cur << 4) | w.pend; w.sp += 1u; }
@@ -583,7 +579,8 @@ __device__ __forceinline__ void walker_leaf(Walker& w, const DSceneView& sc, Loc
             if (!(t == t)) w.fast = false;
         }
     }
-    w.prim = kNoPrim;
+    w.prim = w.prim2;
+    w.prim2 = kNoPrim;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1118,7 +1115,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
     Walker w;
     w.o = w.d = w.inv = mk(0, 0, 0);
     w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
-    w.next = kEnd; w.prim = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
+    w.next = kEnd; w.prim = kNoPrim; w.prim2 = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
     w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
     w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     size_t idx = kNoRay;
@@ -1224,8 +1221,8 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
             for (;;) {
 #pragma unroll
                 for (int rep = 0; rep < 2; ++rep)
-                    if ((w.next != kEnd) & (w.prim == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
-                const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim == kNoPrim) & w.m32);
+                    if ((w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
+                const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32);
                 if (walking == 0u) break;
                 const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
                 if (__popc(parked) >= tune.prim_batch) break;
