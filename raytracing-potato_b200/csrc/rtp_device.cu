@@ -1327,7 +1327,11 @@ __global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ 
 
 constexpr int kPipeDepth = 3;
 constexpr unsigned kQueueSlots = 64;
-constexpr size_t kChunkRays = 1u << 18;  // 16 MiB of rays per pipeline stage
+static size_t chunk_rays() {  // rays per pipeline stage: 2^18 (16 MiB of rays) unless RTP_CHUNK_LOG2 says otherwise (tuning runs)
+    static const size_t v = [] { const char* e = std::getenv("RTP_CHUNK_LOG2"); const int l = e ? std::atoi(e) : 18; return size_t(1) << std::max(10, std::min(24, l)); }();
+    return v;
+}
+#define kChunkRays (chunk_rays())
 
 struct DeviceScene {
     int device = 0;
