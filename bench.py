@@ -393,8 +393,9 @@ def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream,
     if world > 1:
         dist.all_reduce(rays_rank)
     steps = max(3, min(args.steps, 20))
-    for _ in range(2):
+    for _ in range(3):  # warm-up includes the collective: NCCL sets up its channels for this message size on first use
         scene.render_device(p, cam, acc.data_ptr(), acc.data_ptr() + rh * rw * 3 * 8, stream)
+        rdist.reduce_frame(acc)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
