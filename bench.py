@@ -281,9 +281,14 @@ def main():
         del d3, h3
 
     # --- secondary: C1 render (640x360, 16 spp per rank, depth 8), sample ranges + NCCL sum -----------------------------
-    render = None
+    render = render_c4 = None
     if not args.no_render:
         render = bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream, barrier)
+        sc4 = scenes.demo()
+        scene4 = api.Scene(sc4)
+        render_c4 = bench_render(args, torch, dist, api, A, scene4, sc4, dev, rank, world, stream, barrier, rw=1920, rh=1080, spp_rank=8,
+                                 name="C4 subset: demo scene (glass bunny, Lambert bunny, earthmap sphere, light, metal ground, sky)", max_steps=5)
+        scene4.close()
 
     if rank != 0:
         if world > 1:
@@ -341,6 +346,7 @@ def main():
     }
     if render is not None:
         line["render"] = render
+        line["render_c4"] = render_c4
     if incoherent is not None:
         line["incoherent"] = incoherent
     if not args.no_cpu and world == 1:
@@ -377,10 +383,11 @@ def _camera_rays_numpy(cam, u, v):
     return rays
 
 
-def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream, barrier):
+def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream, barrier, rw=640, rh=360, spp_rank=16, name="C1: bunny Lambert + sky", max_steps=20):
     """C1: bunny Lambert + sky, 640x360, depth 8, 16 spp per rank (weak scaling: world*16 spp in total). Each rank
-    renders its sample range into raw sums; one NCCL all-reduce sums the accumulation buffers; rank 0 divides."""
-    rw, rh, spp_rank, depth = 640, 360, 16, 8
+    renders its sample range into raw sums; one NCCL all-reduce sums the accumulation buffers; rank 0 divides.
+    Also used for the C4 scene (demo scene, 1920x1080) at 8 of its 256 spp per rank."""
+    depth = 8
     spp = spp_rank * world
     cam = api.Camera(rw / rh, sc.camera.fov, sc.camera.focal_dist, sc.camera.lens_radius, sc.camera.transformation)
     acc = torch.zeros((rh * rw * 4,), dtype=torch.float64, device=dev)  # rgb (3*npix) then foreground (npix)
@@ -392,7 +399,7 @@ def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream,
     rays_rank = torch.tensor([float(st.rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(rays_rank)
-    steps = max(3, min(args.steps, 20))
+    steps = max(3, min(args.steps, max_steps))
     for _ in range(3):  # warm-up includes the collective: NCCL sets up its channels for this message size on first use
         scene.render_device(p, cam, acc.data_ptr(), acc.data_ptr() + rh * rw * 3 * 8, stream)
         rdist.reduce_frame(acc)
@@ -410,9 +417,9 @@ def bench_render(args, torch, dist, api, A, scene, sc, dev, rank, world, stream,
     sec = float(ms.item()) * 1e-3 / steps
     paths = rw * rh * spp
     return {
-        "workload": f"C1: bunny Lambert + sky, {rw}x{rh}, {spp_rank} spp per GPU ({spp} total), max depth {depth}",
+        "workload": f"{name}, {rw}x{rh}, {spp_rank} spp per GPU ({spp} total), max depth {depth}",
         "samples_per_s": paths / sec, "mrays_per_s": float(rays_rank.item()) / sec / 1e6, "ms_per_frame": sec * 1e3, "steps": steps,
-        "rays_per_path": float(rays_rank.item()) / paths, "collective": "NCCL all-reduce(sum, f64) of the 640x360x4 accumulation buffer" if world > 1 else "none (1 GPU)",
+        "rays_per_path": float(rays_rank.item()) / paths, "collective": f"NCCL all-reduce(sum, f64) of the {rw}x{rh}x4 accumulation buffer" if world > 1 else "none (1 GPU)",
         "launches_per_frame": int(st.kernel_launches),
     }
 
