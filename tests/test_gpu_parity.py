@@ -482,3 +482,22 @@ def test_device_bvh_order_equals_reference_order(gpu, monkeypatch, name):
     rays = oracle.camera_rays(cam, 96, 96)
     assert_hits_equal_bits(g.hit(rays), o.hit(rays))
     g.close(); gh.close(); o.close()
+
+
+def test_thin_lens_camera(gpu):
+    """render.rs:32-52 with lens_radius > 0: the UnitDisk rejection loop (randomness.rs:21-34) now feeds the ray origin, so the
+    per-path draw count varies; GPU and oracle must stay on the same stream (depth-of-field frame, closest hits of lens rays)"""
+    from rtp_b200.api import Camera
+
+    sc = scenes.demo()
+    c = sc.camera
+    sc.camera = Camera(c.aspect_ratio, c.fov, 3.2, 0.08, c.transformation)
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    ig, fg, sg = g.render(192, 108, 4, seed=8)
+    io, fo, so = o.render(192, 108, 4, seed=8)
+    rep = image_report(ig, io)
+    assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+    assert (fg == fo).all() and sg.paths == so.paths
+    sharp, _, _ = g.render(192, 108, 4, seed=8, camera=Camera(c.aspect_ratio, c.fov, 3.2, 0.0, c.transformation))
+    assert not np.array_equal(sharp, ig)  # the lens does something
+    g.close(); o.close()
