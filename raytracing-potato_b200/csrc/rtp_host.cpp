@@ -14,6 +14,7 @@
 #include <fstream>
 #include <future>
 #include <limits>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -37,6 +38,22 @@ static inline double max_num(double a, double b) { return std::fmax(a, b); }
 
 // nalgebra 0.29 reductions on static 3-vectors: (x*x' + y*y') + z*z'
 static inline double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+// Runs fn(begin, end) over [0, n) in contiguous chunks on the host cores (scene flattening of multi-million-leaf scenes).
+template <class F>
+static void parallel_chunks(size_t n, F fn) {
+    const size_t hw = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+    const size_t workers = n < 262144 ? 1 : hw;
+    if (workers == 1) { fn(size_t(0), n); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (n + workers - 1) / workers;
+    for (size_t w = 0; w < workers; ++w) {
+        const size_t b = w * per, e = std::min(n, b + per);
+        if (b >= e) break;
+        pool.emplace_back([=] { fn(b, e); });
+    }
+    for (std::thread& t : pool) t.join();
+}
 
 // --------------------------------------------------------------------------- BVH build --------
 
@@ -202,79 +219,131 @@ static void round_out(const double* bmin, const double* bmax, float* lo, float* 
     }
 }
 
-static void build_wide(FlatScene* out) {
-    const std::vector<DNode>& bn = out->nodes;
-    std::vector<DWide>& wide = out->wide;
-    std::vector<double>& boxes = out->wide_boxes;
-    wide.clear(); boxes.clear();
-    out->wide_depth = 0;
-    auto half_area = [&](uint32_t b) {
+struct WideBuilder {
+    const std::vector<DNode>& bn;
+    size_t defer_leaves = 0;  // > 0: subtrees of at most this many leaves are recorded in `deferred` instead of being built
+    std::vector<DWide> wide;
+    std::vector<double> boxes;  // 24 doubles per wide node: the exact f64 child boxes
+    uint32_t depth = 0;
+    struct Deferred { uint32_t bnode, parent, slot, depth; };
+    std::vector<Deferred> deferred;
+
+    double half_area(uint32_t b) const {
         const double dx = bn[b].bmax[0] - bn[b].bmin[0], dy = bn[b].bmax[1] - bn[b].bmin[1], dz = bn[b].bmax[2] - bn[b].bmin[2];
         const double a = dx * dy + dy * dz + dz * dx;
         return a == a ? a : std::numeric_limits<double>::infinity();
-    };
-    struct Todo { uint32_t bnode, wnode, depth; };
-    std::vector<Todo> todo;
-    wide.emplace_back();
-    todo.push_back({0u, 0u, 1u});
-    while (!todo.empty()) {
-        const Todo t = todo.back();
-        todo.pop_back();
-        out->wide_depth = std::max(out->wide_depth, t.depth);
-        uint32_t kids[4];
-        int nk = 0;
-        if (bn[t.bnode].prim != kNoPrim) {
-            kids[nk++] = t.bnode;  // a one-leaf scene: the root holds that leaf as its only child
-        } else {
-            kids[nk++] = t.bnode + 1;
-            kids[nk++] = bn[t.bnode + 1].skip;
-            while (nk < 4) {
-                int pick = -1;
-                double best = -1.0;
-                for (int k = 0; k < nk; ++k)
-                    if (bn[kids[k]].prim == kNoPrim) {
-                        const double a = half_area(kids[k]);
-                        if (a > best) { best = a; pick = k; }
-                    }
-                if (pick < 0) break;
-                const uint32_t b = kids[pick];
-                for (int k = nk; k > pick + 1; --k) kids[k] = kids[k - 1];
-                kids[pick] = b + 1;
-                kids[pick + 1] = bn[b + 1].skip;
-                ++nk;
-            }
-        }
-        DWide w;
-        std::memset(&w, 0, sizeof w);
-        double b64[4][6];
-        for (int k = 0; k < 4; ++k) {
-            if (k < nk) {
-                const DNode& c = bn[kids[k]];
-                float lo[3], hi[3];
-                round_out(c.bmin, c.bmax, lo, hi);
-                for (int a = 0; a < 3; ++a) { w.plane[a][0][k] = lo[a]; w.plane[a][1][k] = hi[a]; b64[k][a] = c.bmin[a]; b64[k][3 + a] = c.bmax[a]; }
-                if (c.prim != kNoPrim) {
-                    w.child[k] = kWideLeaf | (c.kind << 30) | c.prim;
-                } else {
-                    const uint32_t wi = static_cast<uint32_t>(wide.size());
-                    wide.emplace_back();
-                    w.child[k] = wi;
-                    todo.push_back({kids[k], wi, t.depth + 1});
-                }
-            } else {
-                for (int a = 0; a < 3; ++a) {
-                    w.plane[a][0][k] = std::numeric_limits<float>::infinity();
-                    w.plane[a][1][k] = -std::numeric_limits<float>::infinity();
-                    b64[k][a] = std::numeric_limits<double>::infinity(); b64[k][3 + a] = -std::numeric_limits<double>::infinity();
-                }
-                w.child[k] = kWideEmpty;
-            }
-        }
-        wide[t.wnode] = w;
-        if (boxes.size() < wide.size() * 24) boxes.resize(wide.size() * 24);
-        std::memcpy(&boxes[static_cast<size_t>(t.wnode) * 24], b64, sizeof b64);
     }
-    boxes.resize(wide.size() * 24);
+
+    // builds the subtree under binary node `root_b` into wide[0..), root at index 0
+    void run(uint32_t root_b, uint32_t depth0) {
+        struct Todo { uint32_t bnode, wnode, depth; };
+        std::vector<Todo> todo;
+        wide.emplace_back();
+        todo.push_back({root_b, 0u, depth0});
+        while (!todo.empty()) {
+            const Todo t = todo.back();
+            todo.pop_back();
+            depth = std::max(depth, t.depth);
+            uint32_t kids[4];
+            int nk = 0;
+            if (bn[t.bnode].prim != kNoPrim) {
+                kids[nk++] = t.bnode;  // a one-leaf scene: the root holds that leaf as its only child
+            } else {
+                kids[nk++] = t.bnode + 1;
+                kids[nk++] = bn[t.bnode + 1].skip;
+                while (nk < 4) {
+                    int pick = -1;
+                    double best = -1.0;
+                    for (int k = 0; k < nk; ++k)
+                        if (bn[kids[k]].prim == kNoPrim) {
+                            const double a = half_area(kids[k]);
+                            if (a > best) { best = a; pick = k; }
+                        }
+                    if (pick < 0) break;
+                    const uint32_t b = kids[pick];
+                    for (int k = nk; k > pick + 1; --k) kids[k] = kids[k - 1];
+                    kids[pick] = b + 1;
+                    kids[pick + 1] = bn[b + 1].skip;
+                    ++nk;
+                }
+            }
+            DWide w;
+            std::memset(&w, 0, sizeof w);
+            double b64[4][6];
+            for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+                    const DNode& c = bn[kids[k]];
+                    float lo[3], hi[3];
+                    round_out(c.bmin, c.bmax, lo, hi);
+                    for (int a = 0; a < 3; ++a) { w.plane[a][0][k] = lo[a]; w.plane[a][1][k] = hi[a]; b64[k][a] = c.bmin[a]; b64[k][3 + a] = c.bmax[a]; }
+                    if (c.prim != kNoPrim) {
+                        w.child[k] = kWideLeaf | (c.kind << 30) | c.prim;
+                    } else if (defer_leaves && (static_cast<size_t>(c.skip - kids[k]) + 1) / 2 <= defer_leaves) {
+                        w.child[k] = kWideEmpty;  // patched when the deferred subtrees are appended
+                        deferred.push_back({kids[k], t.wnode, static_cast<uint32_t>(k), t.depth + 1});
+                    } else {
+                        const uint32_t wi = static_cast<uint32_t>(wide.size());
+                        wide.emplace_back();
+                        w.child[k] = wi;
+                        todo.push_back({kids[k], wi, t.depth + 1});
+                    }
+                } else {
+                    for (int a = 0; a < 3; ++a) {
+                        w.plane[a][0][k] = std::numeric_limits<float>::infinity();
+                        w.plane[a][1][k] = -std::numeric_limits<float>::infinity();
+                        b64[k][a] = std::numeric_limits<double>::infinity(); b64[k][3 + a] = -std::numeric_limits<double>::infinity();
+                    }
+                    w.child[k] = kWideEmpty;
+                }
+            }
+            wide[t.wnode] = w;
+            if (boxes.size() < wide.size() * 24) boxes.resize(wide.size() * 24);
+            std::memcpy(&boxes[static_cast<size_t>(t.wnode) * 24], b64, sizeof b64);
+        }
+        boxes.resize(wide.size() * 24);
+    }
+};
+
+static void build_wide(FlatScene* out) {
+    const std::vector<DNode>& bn = out->nodes;
+    const size_t n_leaves = (bn.size() + 1) / 2;
+    // big scenes: the top of the tree is collapsed here, subtrees of <= n/64 leaves on the host cores, then appended in order
+    // (the result does not depend on the number of threads)
+    WideBuilder top{bn, n_leaves >= 262144 ? std::max<size_t>(4096, n_leaves / 64) : 0};
+    top.run(0, 1);
+    std::vector<WideBuilder> subs;
+    subs.reserve(top.deferred.size());
+    for (size_t k = 0; k < top.deferred.size(); ++k) subs.push_back(WideBuilder{bn, 0});
+    if (!subs.empty()) {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        const size_t workers = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+        for (size_t w = 0; w < workers; ++w)
+            pool.emplace_back([&] {
+                for (size_t k = next.fetch_add(1); k < subs.size(); k = next.fetch_add(1)) subs[k].run(top.deferred[k].bnode, top.deferred[k].depth);
+            });
+        for (std::thread& t : pool) t.join();
+    }
+    size_t total = top.wide.size();
+    for (const WideBuilder& sb : subs) total += sb.wide.size();
+    out->wide.swap(top.wide);
+    out->wide_boxes.swap(top.boxes);
+    out->wide.reserve(total);
+    out->wide_boxes.reserve(total * 24);
+    out->wide_depth = top.depth;
+    for (size_t k = 0; k < subs.size(); ++k) {
+        const uint32_t base = static_cast<uint32_t>(out->wide.size());
+        out->wide[top.deferred[k].parent].child[top.deferred[k].slot] = base;
+        for (DWide w : subs[k].wide) {
+            for (int c = 0; c < 4; ++c)
+                if (!(w.child[c] & kWideLeaf)) w.child[c] += base;  // internal child: local index -> global (kWideEmpty has the leaf bit set)
+            out->wide.push_back(w);
+        }
+        out->wide_boxes.insert(out->wide_boxes.end(), subs[k].boxes.begin(), subs[k].boxes.end());
+        out->wide_depth = std::max(out->wide_depth, subs[k].depth);
+        std::vector<DWide>().swap(subs[k].wide);
+        std::vector<double>().swap(subs[k].boxes);
+    }
 }
 
 static bool emit_ok(const rtp_emit& e, uint32_t n_textures) {
@@ -348,19 +417,27 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     // ---- leaf boxes: hittable.rs:124-140 ---------------------------------------------------
     const uint32_t n = d->n_hittables;
     std::vector<BuildItem> items(n);
-    for (uint32_t i = 0; i < n; ++i) {
+    std::atomic<int> first_bad{0};
+    std::string bad_msg;
+    std::mutex bad_lock;
+    auto fail = [&](int code, const std::string& msg) {
+        std::lock_guard<std::mutex> g(bad_lock);
+        if (!first_bad.load()) { first_bad.store(code); bad_msg = msg; }
+    };
+    parallel_chunks(n, [&](size_t lo_i, size_t hi_i) {
+      for (uint32_t i = static_cast<uint32_t>(lo_i); i < hi_i && !first_bad.load(std::memory_order_relaxed); ++i) {
         const rtp_hittable& h = d->hittables[i];
         BuildItem& it = items[i];
         it.id = i;
         if (h.kind == RTP_HITTABLE_SPHERE) {
-            if (h.material >= d->n_materials) return set_error(RTP_ERR_INVALID, "sphere material out of range");
+            if (h.material >= d->n_materials) { fail(RTP_ERR_INVALID, "sphere material out of range"); return; }
             for (int k = 0; k < 3; ++k) {
                 it.bmin[k] = h.center[k] - h.radius;
                 it.bmax[k] = h.center[k] + h.radius;
             }
         } else if (h.kind == RTP_HITTABLE_TRIANGLE) {
             if (h.mesh >= d->n_meshes || static_cast<uint64_t>(h.triangle) + 3 > d->meshes[h.mesh].n_indices)
-                return set_error(RTP_ERR_INVALID, "triangle id out of range");
+                { fail(RTP_ERR_INVALID, "triangle id out of range"); return; }
             const rtp_mesh& m = d->meshes[h.mesh];
             const double* a = m.vertices[m.indices[h.triangle + 0]].position;
             const double* b = m.vertices[m.indices[h.triangle + 1]].position;
@@ -370,15 +447,17 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
                 it.bmax[k] = max_num(max_num(a[k], b[k]), c[k]);
             }
         } else {
-            return set_error(RTP_ERR_UNSUPPORTED, "nested List/Bvh hittables are outside the hot path (DESIGN.md)");
+            { fail(RTP_ERR_UNSUPPORTED, "nested List/Bvh hittables are outside the hot path (DESIGN.md)"); return; }
         }
         if (d->root_kind == RTP_ROOT_BVH)
             for (int k = 0; k < 3; ++k) {
                 double key = 0.5 * (it.bmin[k] + it.bmax[k]);
                 if (key != key)  // partial_cmp().unwrap() panics on NaN (bvh.rs:63)
-                    return set_error(RTP_ERR_INVALID, "NaN bounding-box centroid in hittable " + std::to_string(i));
+                    { fail(RTP_ERR_INVALID, "NaN bounding-box centroid in hittable " + std::to_string(i)); return; }
             }
-    }
+      }
+    });
+    if (first_bad.load()) return set_error(first_bad.load(), bad_msg);
 
     // ---- tree ---------------------------------------------------------------------------------
     out->depth = 0;
@@ -427,7 +506,8 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     out->prims.resize(n);
     out->attrs.resize(n);
     out->leaf_order.resize(n);
-    for (uint32_t slot = 0; slot < n; ++slot) {
+    parallel_chunks(n, [&](size_t lo_s, size_t hi_s) {
+      for (uint32_t slot = static_cast<uint32_t>(lo_s); slot < hi_s; ++slot) {
         uint32_t id = items[slot].id;
         const rtp_hittable& h = d->hittables[id];
         DPrim& p = out->prims[slot];
@@ -462,7 +542,8 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
             }
             p.material = m.material;  // hittable.rs:107
         }
-    }
+      }
+    });
     lap("primitive and attribute records");
     if (d->root_kind == RTP_ROOT_BVH) {
         for (DNode& nd : out->nodes)
