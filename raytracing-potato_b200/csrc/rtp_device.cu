@@ -1420,7 +1420,9 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide, &ds->wide, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide_boxes, &ds->wide_boxes, &ds->bytes)) != RTP_OK) return bail(rc);
-    ds->stack_bytes = static_cast<size_t>(std::max<uint32_t>(flat.wide_depth, 1u)) * 128 * sizeof(uint32_t);
+    // one stack word per tree level and thread; a tree deeper than 96 levels (degenerate geometry) does not get the f32 walk
+    // at all (view.f32_culling below), so its launches carry no stack
+    ds->stack_bytes = static_cast<size_t>(flat.wide_depth <= 96 ? std::max<uint32_t>(flat.wide_depth, 1u) : 1u) * 128 * sizeof(uint32_t);
     if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.materials, &ds->materials, &ds->bytes)) != RTP_OK) return bail(rc);

@@ -501,3 +501,36 @@ def test_thin_lens_camera(gpu):
     sharp, _, _ = g.render(192, 108, 4, seed=8, camera=Camera(c.aspect_ratio, c.fov, 3.2, 0.0, c.transformation))
     assert not np.array_equal(sharp, ig)  # the lens does something
     g.close(); o.close()
+
+
+@pytest.mark.parametrize("scale,shift", [(1.0, 0.0), (1e9, 3e12), (1e-9, 0.0), (1e6, -7e13), (1e-3, 4e14)])
+def test_f32_culling_error_budget_at_extreme_magnitudes(gpu, scale, shift):
+    """DESIGN.md §4 at the edges of its preconditions: the bunny scaled / translated so that coordinates reach 1e12..1e14 (where
+    an f32 ulp is thousands of units and the culling boxes inflate accordingly) or shrink to 1e-9, and rays whose direction
+    components span 13 orders of magnitude. The conservative test may stop culling, but it must never reject a box the exact
+    test accepts (violation counter 0) and the hits must stay the oracle's bits."""
+    import torch
+
+    sc = scenes.bunny_triangles_only()
+    m = sc.scene_data.mesh_table[0]
+    m.vertices["position"] = m.vertices["position"] * scale + shift
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    rng = np.random.default_rng(11)
+    n = 60000
+    lo, hi = m.vertices["position"].min(axis=0), m.vertices["position"].max(axis=0)
+    centre, ext = 0.5 * (lo + hi), (hi - lo).max()
+    origin = centre + rng.normal(size=(n, 3)) * ext * 2.0
+    target = lo + rng.random((n, 3)) * (hi - lo)
+    d = target - origin
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[: n // 4] *= 10.0 ** rng.uniform(-12, 12, size=(n // 4, 1))                 # non-unit directions, |d| from 1e-12 to 1e12
+    skew = slice(n // 4, n // 2)
+    d[skew] *= 10.0 ** rng.uniform(-13, 0, size=(n // 4, 3))                     # components 13 orders of magnitude apart
+    rays = np.zeros(n, dtype=A.RAY_DTYPE)
+    rays["origin"], rays["direction"], rays["t_min"], rays["t_max"] = origin, d, 1e-3 * min(scale, 1.0), np.inf
+    assert_hits_equal_bits(g.hit(rays), o.hit(rays))
+    d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((n, 2), dtype=torch.float64, device="cuda")
+    st = g.hit_device_counted(d_rays.data_ptr(), n, d_hits.data_ptr())
+    assert st.conservative_violations == 0 and st.node_visits > 0
+    g.close(); o.close()
