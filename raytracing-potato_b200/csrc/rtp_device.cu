@@ -1644,7 +1644,8 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
     // samples per launch: about 8 Mi paths (scratch 256 MiB; wavefront queues 176 B + 48 B x max_bounce per path, so the
     // path budget shrinks for deep stacks to keep the queues under ~4 GiB)
     const bool wave = !ds->use_simple_render;
-    const size_t path_budget = wave ? std::min<size_t>(size_t(8) << 20, (size_t(4) << 30) / (176 + 48 * static_cast<size_t>(p->max_bounce))) : (size_t(8) << 20);
+    size_t path_budget = wave ? std::min<size_t>(size_t(8) << 20, (size_t(4) << 30) / (176 + 48 * static_cast<size_t>(p->max_bounce))) : (size_t(8) << 20);
+    if (const char* v = std::getenv("RTP_PATH_BUDGET")) path_budget = std::max<size_t>(1, static_cast<size_t>(std::atoll(v)));  // tests: force several launches per frame
     uint32_t per_launch = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(ns_total ? ns_total : 1, path_budget / npix)));
     const size_t need = npix * per_launch;
     if (wave && ns_total) {

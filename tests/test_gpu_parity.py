@@ -534,3 +534,45 @@ def test_f32_culling_error_budget_at_extreme_magnitudes(gpu, scale, shift):
     st = g.hit_device_counted(d_rays.data_ptr(), n, d_hits.data_ptr())
     assert st.conservative_violations == 0 and st.node_visits > 0
     g.close(); o.close()
+
+
+def test_frames_split_into_several_launches_sum_in_sample_order(gpu, monkeypatch):
+    """a frame whose paths exceed the per-launch budget (C4: 64 launches of 4 spp) is traced in several launches whose samples
+    are added to the per-pixel sums in sample order (main.rs:78-87): forcing 1, 2 or 3 spp per launch must not change a bit"""
+    sc = scenes.glass_bunny()
+    g = api.Scene(sc)
+    w, h, spp = 96, 54, 7
+    ref, fref, sref = g.render(w, h, spp, seed=12)
+    for budget in (w * h, 2 * w * h, 3 * w * h + 5):
+        monkeypatch.setenv("RTP_PATH_BUDGET", str(budget))
+        img, fg, st = g.render(w, h, spp, seed=12)
+        assert img.tobytes() == ref.tobytes() and fg.tobytes() == fref.tobytes() and st.rays == sref.rays
+        assert st.kernel_launches > sref.kernel_launches
+    monkeypatch.delenv("RTP_PATH_BUDGET")
+    g.close()
+
+
+@pytest.mark.parametrize("kind", ["one_sphere_bvh", "one_triangle_bvh", "empty_list", "one_sphere_list"])
+def test_degenerate_scene_sizes(gpu, kind):
+    """the smallest scenes: a Bvh over a single leaf (the culling tree is one node with one child), and List roots with zero and
+    one primitive (every ray of the empty list misses and shades the background)"""
+    sc = scenes.one_triangle()
+    if kind == "one_sphere_bvh":
+        sc.hittables = api.Hittable.Sphere([0.0, 0.0, 0.0], 0.7, 1)
+    elif kind == "one_triangle_bvh":
+        sc.hittables = api.Hittable.Triangle(0, 0)
+    elif kind == "empty_list":
+        sc.root_kind, sc.hittables = "list", sc.hittables[:0]
+    else:
+        sc.root_kind, sc.hittables = "list", api.Hittable.Sphere([0.0, 0.0, 0.0], 0.7, 1)
+    sc.hittables = np.atleast_1d(sc.hittables)
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    cam = api.Camera(1.0, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+    rays = oracle.camera_rays(cam, 64, 64)
+    assert_hits_equal_bits(g.hit(rays), o.hit(rays))
+    ig, fg, sg = g.render(48, 48, 3, seed=2)
+    io, fo, so = o.render(48, 48, 3, seed=2)
+    rep = image_report(ig, io)
+    assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+    assert (fg == fo).all() and sg.rays == so.rays
+    g.close(); o.close()
