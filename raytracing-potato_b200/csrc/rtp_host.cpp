@@ -485,8 +485,17 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
         lap("reference median-split order (Bvh::new)");
         out->depth = b.depth.load();
         out->n_reference_nodes = static_cast<uint32_t>(out->nodes.size());
+        // The freedom to re-shape the tree rests on ordered, finite leaf boxes (min <= max on every axis: a
+        // parent's slab interval then contains each child's). A sphere of negative radius has an INVERTED box (hittable.rs:124-131
+        // computes center -/+ radius), which AABB::collide still treats like the proper box but AABB::union does not, so what the
+        // reference returns for such a scene depends on its own topology: keep that topology and the literal slab test.
+        bool regular = true;
+        for (const BuildItem& it : items)
+            for (int k = 0; k < 3; ++k)
+                if (!(it.bmin[k] <= it.bmax[k]) || !std::isfinite(it.bmin[k]) || !std::isfinite(it.bmax[k])) regular = false;
+        if (!regular) out->boxes_finite = false;
         const char* tree = std::getenv("RTP_TREE");  // "reference" keeps the median-split topology on the device (A/B runs, counter parity)
-        if (!(tree && std::string(tree) == "reference")) {
+        if (regular && !(tree && std::string(tree) == "reference")) {
             SeqBuilder sb{items, out->nodes};
             sb.build(0, n, 0, 1, 4);
             out->device_depth = sb.depth.load();

@@ -127,7 +127,8 @@ struct FlatScene {
     uint32_t n_reference_nodes = 0;  // 2n-1
     uint32_t device_depth = 0;       // of the culling tree the kernels walk
     double scene_mag = 0.0;    // largest |coordinate| of any node box
-    bool boxes_finite = true;  // every node box coordinate is finite (precondition of the sign-selected slab test)
+    bool boxes_finite = true;  // every box is finite and ordered (min <= max): precondition of the sign-selected slab test, of the
+                               // f32 culling walk and of re-shaping the tree; otherwise the reference topology and the literal test are used
     rtp_emit background{};
 };
 

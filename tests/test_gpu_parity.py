@@ -576,3 +576,62 @@ def test_degenerate_scene_sizes(gpu, kind):
     assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
     assert (fg == fo).all() and sg.rays == so.rays
     g.close(); o.close()
+
+
+def test_exact_ties_and_degenerate_primitives(gpu):
+    """coincident triangles hit at exactly the same t: the reference keeps the LATER one in depth-first order (bvh.rs:108,111 and
+    hittable.rs:99 accept t == t_max). Every triangle of a small grid appears three times, plus zero-area triangles, a
+    zero-radius and a negative-radius sphere and a sphere nested exactly inside another; ids must be the oracle's."""
+    pos, idx = [], []
+    for k, (x, y) in enumerate((x, y) for x in range(-6, 6) for y in range(-6, 6)):
+        for _ in range(3):  # the same triangle three times, with its own vertices
+            base = len(pos)
+            pos += [[x, y, 0.0], [x + 1.0, y, 0.0], [x, y + 1.0, 0.25 * ((x + y) % 3)]]
+            idx += [base, base + 1, base + 2]
+    base = len(pos)
+    pos += [[0.0, 0.0, 1.0], [1.0, 1.0, 1.0], [2.0, 2.0, 1.0], [3.0, 0.0, 1.0], [3.0, 0.0, 1.0], [3.0, 0.0, 1.0]]  # collinear, and a point
+    idx += [base, base + 1, base + 2, base + 3, base + 4, base + 5]
+    mesh = api.Mesh.from_arrays(pos, indices=idx, material=0)
+    sc = scenes.one_triangle()
+    sc.scene_data.mesh_table[:] = [mesh]
+    sc.hittables = api.Hittable.concat([api.Hittable.triangles_of(mesh, 0), api.Hittable.Sphere([0.5, 0.5, 2.0], 0.0, 1),
+                                        api.Hittable.Sphere([-2.0, 1.0, 2.0], -0.5, 1), api.Hittable.Sphere([2.0, -2.0, 1.5], 0.6, 1),
+                                        api.Hittable.Sphere([2.0, -2.0, 1.5], 0.6, 0)])
+    g, o = api.Scene(sc), oracle.Scene(sc)
+    rng = np.random.default_rng(5)
+    n = 40000
+    rays = np.zeros(n, dtype=A.RAY_DTYPE)
+    rays["origin"] = np.stack([rng.uniform(-7, 7, n), rng.uniform(-7, 7, n), np.full(n, 5.0)], axis=1)
+    target = np.stack([rng.uniform(-6, 6, n), rng.uniform(-6, 6, n), np.zeros(n)], axis=1)
+    d = target - rays["origin"]
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["direction"][: n // 8] = [0.0, 0.0, -1.0]  # axis-parallel: the exact walk
+    rays["t_min"], rays["t_max"] = 1e-3, np.inf
+    hg, ho = g.hit(rays), o.hit(rays)
+    assert_hits_equal_bits(hg, ho)
+    tri_hits = ho["leaf"][ho["leaf"] < len(idx) // 3 - 2]
+    assert len(tri_hits) > n // 4
+    for root in ("bvh", "list"):
+        sc.root_kind = root
+        gl, ol = api.Scene(sc), oracle.Scene(sc)
+        assert_hits_equal_bits(gl.hit(rays[:8000]), ol.hit(rays[:8000]))
+        gl.close(); ol.close()
+    g.close(); o.close()
+    # non-finite geometry: an infinite-radius sphere and a triangle with a vertex at infinity (infinite, not NaN, centroids)
+    sc.root_kind = "bvh"
+    good = sc.hittables
+    sc.hittables = api.Hittable.concat([good, api.Hittable.Sphere([0.0, 0.0, -3.0], np.inf, 1)])
+    with pytest.raises(api.RtpError) as e:  # its centroid is inf - inf = NaN: partial_cmp().unwrap() panics (bvh.rs:63)
+        api.Scene(sc)
+    assert e.value.code == A.ERR_INVALID
+    pos2 = pos + [[0.0, 0.0, 1.5], [np.inf, 0.0, 1.5], [0.0, 1.0, 1.5]]
+    idx2 = idx + [len(pos), len(pos) + 1, len(pos) + 2]
+    mesh2 = api.Mesh.from_arrays(pos2, indices=idx2, material=0)
+    sc.scene_data.mesh_table[:] = [mesh2]
+    sc.hittables = api.Hittable.concat([api.Hittable.triangles_of(mesh2, 0), good[good["kind"] == 0]])
+    gi, oi = api.Scene(sc), oracle.Scene(sc)
+    hgi, hoi = gi.hit(rays[:8000]), oi.hit(rays[:8000])
+    assert (hgi["leaf"] == hoi["leaf"]).all()
+    both_nan = np.isnan(hgi["t"]) & np.isnan(hoi["t"])  # a NaN t is accepted by hittable.rs:99 (every comparison is false); payload bits are not pinned
+    assert ((hgi["t"].view(np.uint64) == hoi["t"].view(np.uint64)) | both_nan).all()
+    gi.close(); oi.close()
