@@ -516,17 +516,21 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
         const uint4 ch = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(sc.wide + w.cur) + 96u));
         w.c0 = ch.x; w.c1 = ch.y; w.c2 = ch.z; w.c3 = ch.w;
     }
+    // hand out the lowest pending child; everything below is selects and one predicated store, no branches
     const uint32_t k = __ffs(w.pend) - 1u;
     w.pend &= w.pend - 1u;
-    const uint32_t c = k == 0u ? w.c0 : (k == 1u ? w.c1 : (k == 2u ? w.c2 : w.c3));
-    if (c & kWideLeaf) {
-        const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
-        if (w.prim == kNoPrim) w.prim = leaf; else w.prim2 = leaf;
-        w.need_gate = true;
-    } else {
-        if (w.pend) { stack[w.sp * stride] = (w.cur << 4) | w.pend; w.sp += 1u; }
-        w.next = c;
-    }
+    const uint32_t s1 = (k & 1u) << 5;  // clamped funnel shifts pick one of four 32-bit words
+    const uint32_t c = __funnelshift_rc(__funnelshift_rc(w.c0, w.c1, s1), __funnelshift_rc(w.c2, w.c3, s1), (k & 2u) << 4);
+    const bool is_leaf = (c & kWideLeaf) != 0u;
+    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+    const bool first = w.prim == kNoPrim;
+    w.prim2 = (is_leaf & !first) ? leaf : w.prim2;
+    w.prim = (is_leaf & first) ? leaf : w.prim;
+    w.need_gate = w.need_gate | is_leaf;
+    const bool push = !is_leaf & (w.pend != 0u);
+    if (push) stack[w.sp * stride] = (w.cur << 4) | w.pend;
+    w.sp += push ? 1u : 0u;
+    w.next = is_leaf ? kNone : c;
 }
 
 // One exact f64 step for lanes outside the f32 path's preconditions (bvh.rs:93-119 literally, or collide_fast).
