@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RTP_ABI_VERSION 1u
+#define RTP_ABI_VERSION 2u
 
 typedef enum rtp_status {
     RTP_OK = 0,
@@ -216,6 +216,7 @@ typedef struct rtp_stats {
     uint64_t conservative_violations; /* f32 culling decisions that contradicted the f64 test: must be 0 */
     double device_ms;       /* CUDA-event time of the device work of this call             */
     uint64_t kernel_launches;
+    uint64_t order_rewalks; /* any-order walk: rays walked again in the reference's order (counting kernels only) */
 } rtp_stats;
 
 typedef struct rtp_scene_info {

@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MISS = 0xFFFFFFFF
 
 # rtp_status
@@ -137,6 +137,7 @@ class Stats(C.Structure):
         ("conservative_violations", C.c_uint64),
         ("device_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
+        ("order_rewalks", C.c_uint64),
     ]
 
     def as_dict(self):

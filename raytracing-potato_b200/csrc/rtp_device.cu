@@ -60,11 +60,11 @@ __device__ __forceinline__ D3 normalize(D3 a) {
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 struct Counters {
-    unsigned long long rays, paths, node_visits, triangle_tests, sphere_tests, leaf_gates, violations;
+    unsigned long long rays, paths, node_visits, triangle_tests, sphere_tests, leaf_gates, violations, rewalks;
 };
 
 struct LocalCounters {
-    unsigned int rays, node_visits, triangle_tests, sphere_tests, leaf_gates, violations;
+    unsigned int rays, node_visits, triangle_tests, sphere_tests, leaf_gates, violations, rewalks;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -361,7 +361,7 @@ __device__ __forceinline__ void write_hit(const DSceneView& sc, void* __restrict
 template <bool COUNT>
 __device__ __forceinline__ void flush_counters(Counters* counters, const LocalCounters& lc) {
     if (!counters) return;
-    unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests, lg = lc.leaf_gates, vi = lc.violations;
+    unsigned int r = lc.rays, nv = lc.node_visits, tt = lc.triangle_tests, st = lc.sphere_tests, lg = lc.leaf_gates, vi = lc.violations, rw = lc.rewalks;
     for (int off = 16; off; off >>= 1) {
         r += __shfl_down_sync(0xffffffffu, r, off);
         if (COUNT) {
@@ -370,6 +370,7 @@ __device__ __forceinline__ void flush_counters(Counters* counters, const LocalCo
             st += __shfl_down_sync(0xffffffffu, st, off);
             lg += __shfl_down_sync(0xffffffffu, lg, off);
             vi += __shfl_down_sync(0xffffffffu, vi, off);
+            rw += __shfl_down_sync(0xffffffffu, rw, off);
         }
     }
     if ((threadIdx.x & 31) == 0) {
@@ -380,6 +381,7 @@ __device__ __forceinline__ void flush_counters(Counters* counters, const LocalCo
             atomicAdd(&counters->sphere_tests, static_cast<unsigned long long>(st));
             atomicAdd(&counters->leaf_gates, static_cast<unsigned long long>(lg));
             atomicAdd(&counters->violations, static_cast<unsigned long long>(vi));
+            if (rw) atomicAdd(&counters->rewalks, static_cast<unsigned long long>(rw));
         }
     }
 }
@@ -389,7 +391,7 @@ template <bool COUNT, bool FULL>
 __global__ void __launch_bounds__(128) trace_closest_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                             Counters* counters) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
     if (i < n) {
         const double2* rp = reinterpret_cast<const double2*>(rays + i);
         const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
@@ -434,6 +436,12 @@ struct Tuning {
 //   entries in shared memory holds the ancestors that still have pending children.
 //   Other lanes (non-finite or axis-parallel rays, huge coordinates, List roots) walk the exact f64 pre-order tree with
 //   `next` as the pre-order index (bvh.rs:93-119 literally).
+#ifndef RTP_ANY_BLOCKS
+#define RTP_ANY_BLOCKS 5
+#endif
+#ifndef RTP_ANY_POPS
+#define RTP_ANY_POPS 1
+#endif
 constexpr uint32_t kEnd = 0xFFFFFFFFu;   // `next`: the walk is over
 constexpr uint32_t kNone = 0xFFFFFFFEu;  // `next`: no node to visit, take the next pending child
 struct Walker {
@@ -452,6 +460,12 @@ struct Walker {
     bool m32;        // eligible for the f32 culling walk
     bool need_gate;  // parked by the f32 walk: the leaf's exact f64 gate has not been evaluated yet
     bool sx, sy, sz;
+    // any-order walk (walker_step_any): `any` = this lane is in that mode; T_win = the window top min(ray.t_max, t_best +
+    // 2 slack(t_best)) that culls boxes and bounds the primitive tests; A_min = smallest t of a tested leaf that passes its
+    // static tests but whose own box entry lies above its t (its acceptance depends on the reference's visiting order)
+    bool any;
+    double T_win, A_min;
+    float s0f, s1f;  // slack(t) = s0f + s1f |t|, rounded up
 };
 
 // utility.rs:71-77 Ray::expand plus the derived quantities of the fast paths
@@ -479,6 +493,7 @@ __device__ __forceinline__ void walker_start(Walker& w, const DSceneView& sc, co
     w.pend = 0; w.sp = 0; w.cur = 0;
     w.prim = kNoPrim; w.prim2 = kNoPrim;
     w.need_gate = false;
+    w.any = false;
 }
 
 // One step of an f32-eligible lane that is walking (next != kEnd, not parked): visit `next` if there is one (four
@@ -531,6 +546,160 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
     if (push) stack[w.sp * stride] = (w.cur << 4) | w.pend;
     w.sp += push ? 1u : 0u;
     w.next = is_leaf ? kNone : c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Any-order walk. The reference's result is that of the sequential process
+//     T = ray.t_max; for leaf p in DFS order: if T >= m_p: T = t_p, best = p
+// where, for a leaf that passes its static tests (box entered at all, barycentrics inside, t_p >= t_min), t_p is the computed
+// hit distance and m_p = max(t_p, computed slab entry of p's own box) — both independent of T. A leaf is NORMAL when
+// m_p = t_p and ABNORMAL when rounding put t_p below its own box entry. If every leaf with t_p <= M + 2 slack is normal, where
+// M is the smallest m_p, the process returns min t_p, ties to the larger DFS rank — no matter in which order the leaves are
+// looked at. slack(t) bounds m_p - t_p for every triangle that is not "big" (error analysis of hittable.rs:77-95 in DESIGN.md
+// §4b), so a box whose conservative entry lies above T_win = t_best + 2 slack(t_best) holds no leaf that can matter and is
+// skipped, children are visited nearest first, and the primitive tests use T_win as their upper bound. Big primitives (spheres,
+// outsized triangles) are tested for every ray before the walk. A ray that met an abnormal leaf inside the final window is
+// walked again in the reference's order (walker_step_wide): exactness never rests on the bound being tight, only on it
+// being a bound.
+// ---------------------------------------------------------------------------------------------
+
+// per-ray slack coefficients; false: the ray is not eligible (bounds not self-consistent, or not finite)
+__device__ __forceinline__ bool any_slack(const Walker& w, const DSceneView& sc, float& s0f, float& s1f) {
+    const double u = 0x1.0p-53, K = 8.0 * u * 1e7;  // |det| >= 1e-7 (hittable.rs:80), 8u: rounding of a 6-term sum of products
+    const double P = fmax(fmax(fabs(w.o.x), fabs(w.o.y)), fabs(w.o.z)) + sc.any_A;
+    const double D = fmax(fmax(fabs(w.d.x), fabs(w.d.y)), fabs(w.d.z));
+    const double I = fmax(fmax(fabs(w.inv.x), fabs(w.inv.y)), fabs(w.inv.z));
+    const double E = sc.any_E;
+    const double kappa = K * 6.0 * D * E * E;
+    const double e_uv = K * (6.0 * P * E * D + 6.06 * D * E * E) + 3.0 * u;
+    if (!(kappa <= 0.25) || !(e_uv <= 0.01)) return false;
+    const double eta = (4.0 * e_uv + 5.0 * u) * E;
+    const double s0 = 4.0 * ((eta + u * P) * I * (1.0 + u) + K * 6.0 * P * E * E / (1.0 - kappa) + 3.0 * u * fabs(w.tmin));
+    const double s1 = 4.0 * ((K * 6.0 * D * E * E + 5.0 * u) / (1.0 - kappa));
+    s0f = __double2float_ru(s0); s1f = __double2float_ru(s1);
+    return s0f <= 3.0e38f && s1f <= 3.0e38f;
+}
+
+// exact test of one leaf in any-order mode: static tests with the window top as the upper bound, then classification
+template <bool COUNT>
+__device__ __forceinline__ void any_test(Walker& w, const DSceneView& sc, LocalCounters& lc, uint32_t prim) {
+    const uint32_t slot = prim & 0x7FFFFFFFu, kind = prim >> 31;
+    const DPrim* p = sc.prims + slot;
+    double t, u = 0.0, v = 0.0;
+    bool hit;
+    if (kind == RTP_HITTABLE_TRIANGLE) {
+        if (COUNT) lc.triangle_tests++;
+        hit = test_triangle(p, w.o, w.d, w.tmin, w.T_win, t, u, v);
+    } else {
+        if (COUNT) lc.sphere_tests++;
+        hit = test_sphere(p, w.o, w.d, w.tmin, w.T_win, t);
+    }
+    if (!hit) return;
+    if (!(t == t)) { w.A_min = -CUDART_INF; return; }  // NaN t (overflowing geometry): let the in-order walk decide
+    const double* pb = p->bmin;
+    const double2 b0 = ldg2(pb), b1 = ldg2(pb + 2), b2 = ldg2(pb + 4);
+    if (COUNT) lc.leaf_gates++;
+    if (collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, t)) {
+        // normal leaf: min t, ties to the larger DFS rank (= slot)
+        if (w.h.slot == kNoPrim || t < w.h.t || (t == w.h.t && slot > w.h.slot)) {
+            w.h.t = t; w.h.u = u; w.h.v = v; w.h.slot = slot; w.h.kind = kind;
+            const double win = t + 2.0 * (static_cast<double>(w.s0f) + static_cast<double>(w.s1f) * fabs(t));
+            w.T_win = fmin(w.T_win, win);
+            w.r32.T_up = __double2float_ru(w.T_win);
+        }
+    } else if (collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, CUDART_INF)) {
+        w.A_min = fmin(w.A_min, t);  // abnormal: its box is entered, but only after t
+    }
+}
+
+// switch a freshly started lane (walker_start) to any-order mode if scene and ray allow it, and test the big primitives
+template <bool COUNT>
+__device__ __forceinline__ void any_begin(Walker& w, const DSceneView& sc, LocalCounters& lc) {
+    w.any = false;
+    if (!(sc.any_order != 0u && w.m32 && w.tmin >= 0.0)) return;
+    if (!any_slack(w, sc, w.s0f, w.s1f)) return;
+    w.any = true;
+    w.T_win = w.h.t;
+    w.A_min = CUDART_INF;
+    for (uint32_t b = 0; b < sc.n_big; ++b) {
+        // a big primitive whose own box the ray never enters fails the reference's leaf gate for every t_max (bvh.rs:96): skip it
+        const double* pb = sc.prims[sc.big[b] & 0x7FFFFFFFu].bmin;
+        if (COUNT) lc.leaf_gates++;
+        if (collide_fast(ldg2(pb), ldg2(pb + 2), ldg2(pb + 4), w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, CUDART_INF)) any_test<COUNT>(w, sc, lc, sc.big[b]);
+    }
+}
+
+__device__ __forceinline__ void any_park(Walker& w, uint32_t c) {
+    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+    const bool first = w.prim == kNoPrim;
+    w.prim2 = first ? w.prim2 : leaf;
+    w.prim = first ? leaf : w.prim;
+}
+
+// One step of a lane in any-order mode: take a node (the pending one, else the nearest postponed entry that survives the
+// window), test its four children, postpone the farther ones with their entry distance, go on with the nearest. `stack` is
+// this thread's column of (child word, entry distance) pairs.
+template <bool COUNT>
+__device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc, LocalCounters& lc, uint2* __restrict__ stack, uint32_t stride) {
+    if (w.next == kNone) {
+        uint2 e;
+#pragma unroll 1
+        for (int tries = 0;; ++tries) {
+            if (w.sp == 0u) { w.next = kEnd; return; }
+            w.sp -= 1u;
+            e = stack[w.sp * stride];
+            if (__uint_as_float(e.y) <= w.r32.T_up) break;  // else: the window shrank since this entry was postponed
+            if (tries + 1 == RTP_ANY_POPS) return;
+        }
+        if (e.x & kWideLeaf) { any_park(w, e.x); return; }
+        w.next = e.x;
+    }
+    const char* np = reinterpret_cast<const char*>(sc.wide + w.next);
+    const float4 nx4 = __ldg(reinterpret_cast<const float4*>(np + w.onx));
+    const float4 fx4 = __ldg(reinterpret_cast<const float4*>(np + (16u - w.onx)));
+    const float4 ny4 = __ldg(reinterpret_cast<const float4*>(np + 32u + w.ony));
+    const float4 fy4 = __ldg(reinterpret_cast<const float4*>(np + 32u + (16u - w.ony)));
+    const float4 nz4 = __ldg(reinterpret_cast<const float4*>(np + 64u + w.onz));
+    const float4 fz4 = __ldg(reinterpret_cast<const float4*>(np + 64u + (16u - w.onz)));
+    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 96u));
+    const uint32_t big = __ldg(reinterpret_cast<const uint32_t*>(np + 112u));
+    const Ray32& r = w.r32;
+    // key = entry distance (non-negative float: its bits order like the value) with the child index in the two low bits;
+    // children that are missed, beyond the window, empty or big get the largest key
+#define RTP_KEY(c, idx)                                                                                                        \
+    const float n##c = fmaxf(fmaxf(fmaf(nx4.c, r.ix, r.clx), fmaf(ny4.c, r.iy, r.cly)), fmaxf(fmaf(nz4.c, r.iz, r.clz), r.tmin_dn)); \
+    const float f##c = fminf(fminf(fmaf(fx4.c, r.ix, r.chx), fmaf(fy4.c, r.iy, r.chy)), fminf(fmaf(fz4.c, r.iz, r.chz), r.T_up));    \
+    const uint32_t k##c = (f##c >= n##c && !((big >> idx) & 1u)) ? ((__float_as_uint(n##c) & ~3u) | idx) : 0xFFFFFFFFu;
+    RTP_KEY(x, 0u) RTP_KEY(y, 1u) RTP_KEY(z, 2u) RTP_KEY(w, 3u)
+#undef RTP_KEY
+    if (COUNT) {
+        lc.node_visits++;
+        const double* b64 = sc.wide_boxes + static_cast<size_t>(w.next) * 24;
+        const uint32_t keys[4] = {kx, ky, kz, kw};
+        for (uint32_t k = 0; k < 4; ++k)  // a rejected child must fail the exact test with the window top as t_max
+            if (keys[k] == 0xFFFFFFFFu && !((big >> k) & 1u) && (&ch.x)[k] != kWideEmpty &&
+                collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), w.o, w.inv, w.tmin, w.T_win))
+                lc.violations++;
+    }
+    // sorting network for four keys
+    const uint32_t a0 = min(kx, ky), a1 = max(kx, ky), b0 = min(kz, kw), b1 = max(kz, kw);
+    const uint32_t s0 = min(a0, b0), m0 = max(a0, b0), m1 = min(a1, b1), s3 = max(a1, b1);
+    const uint32_t s1 = min(m0, m1), s2 = max(m0, m1);
+#define RTP_SEL(k) __funnelshift_rc(__funnelshift_rc(ch.x, ch.y, ((k) & 1u) << 5), __funnelshift_rc(ch.z, ch.w, ((k) & 1u) << 5), ((k) & 2u) << 4)
+#define RTP_PUSH(s)                                                                       \
+    if ((s) != 0xFFFFFFFFu) {                                                             \
+        stack[w.sp * stride] = make_uint2(RTP_SEL(s), (s) & ~3u);                         \
+        w.sp += 1u;                                                                       \
+    }
+    RTP_PUSH(s3) RTP_PUSH(s2) RTP_PUSH(s1)
+#undef RTP_PUSH
+    w.next = kNone;
+    if (s0 != 0xFFFFFFFFu) {
+        const uint32_t c = RTP_SEL(s0);
+        if (c & kWideLeaf) any_park(w, c);
+        else w.next = c;
+    }
+#undef RTP_SEL
 }
 
 // One exact f64 step for lanes outside the f32 path's preconditions (bvh.rs:93-119 literally, or collide_fast).
@@ -920,7 +1089,7 @@ __global__ void __launch_bounds__(128) render_paths_kernel(DSceneView sc, DCamer
     const size_t npix = static_cast<size_t>(rp.tile_w) * rp.tile_h;
     const size_t total = npix * rp.n_samples;
     const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
     if (p < total) {
         uint32_t i, j, smp;
         path_coords(rp, p, i, j, smp);
@@ -1095,12 +1264,13 @@ struct TailArgs {
 };
 
 constexpr int kTraceBlocksPerSM = 6;
+constexpr int kTraceBlocksPerSMAny = RTP_ANY_BLOCKS;  // the any-order variant carries both walkers' state
 
-template <bool COUNT, int OUT, bool LIST>
-__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+template <bool COUNT, int OUT, bool LIST, bool ANY>
+__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY ? kTraceBlocksPerSMAny : kTraceBlocksPerSM)) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev,
                                                                   TailArgs ta) {
-    extern __shared__ uint32_t wide_stack[];  // [level][thread]
+    extern __shared__ __align__(16) uint32_t wide_stack[];  // [level][thread]; any-order lanes: [entry][thread] of uint2
     if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
     if (OUT == OUT_TAIL) {
         if (n == 0 || n > ta.threshold) return;  // the trace/shade pair that follows handles this queue
@@ -1109,10 +1279,13 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
     uint4 pst = make_uint4(0, 0, 0, 0);  // tail mode: the path state of the lane's ray (WaveQueues::state)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    uint32_t* const my_stack = wide_stack + threadIdx.x;
+    // any-order kernels: every thread owns a column of uint2 entries; a lane walking in the reference's order (re-walk) keeps
+    // its one-word entries in the .x halves of its own column, so lanes in different modes never touch each other's stack
+    uint32_t* const my_stack = wide_stack + (ANY ? 2u : 1u) * threadIdx.x;
+    uint2* const my_stack2 = reinterpret_cast<uint2*>(wide_stack) + threadIdx.x;
     const uint32_t stride = blockDim.x;
     constexpr size_t kNoRay = ~static_cast<size_t>(0);
-    LocalCounters lc = {0, 0, 0, 0, 0, 0};
+    LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
 
     // lane state: next == kEnd && prim == kNoPrim  -> empty (its finished ray, if any, is written at the next refill);
     //             prim != kNoPrim                  -> parked at a leaf;  otherwise walking
@@ -1121,6 +1294,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
     w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
     w.next = kEnd; w.prim = kNoPrim; w.prim2 = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
     w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
+    w.any = false; w.T_win = 0.0; w.A_min = 0.0; w.s0f = w.s1f = 0.f;
     w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     size_t idx = kNoRay;
     bool more = true;  // warp-uniform: the queue may still hold rays
@@ -1129,6 +1303,18 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
     const int refill_thr = min(tune.refill_min, max(1, lane_cap / 2));
 
     for (;;) {
+        if (ANY) {
+            // an any-order lane whose walk is over: if an abnormal leaf lies inside the final window, the answer may depend on the
+            // reference's visiting order, so the ray is walked again in that order (walker_step_wide)
+            if ((w.next == kEnd) & (w.prim == kNoPrim) & w.any) {
+                w.any = false;
+                if (w.A_min <= w.T_win && w.A_min != CUDART_INF) {
+                    const double t0 = OUT == OUT_TAIL ? CUDART_INF : __ldg(&rays[idx].t_max);
+                    walker_start(w, sc, tune, w.o, w.d, w.tmin, t0);
+                    if (COUNT) lc.rewalks++;
+                }
+            }
+        }
         // ---- retire finished rays and refill ----------------------------------------------------------
         const bool is_done = (w.next == kEnd) & (w.prim == kNoPrim);
         const bool fin = OUT == OUT_TAIL && is_done && idx != kNoRay;  // tail mode: walk over, vertex not shaded yet
@@ -1171,6 +1357,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
                     if (alive) {
                         walker_start(w, sc, tune, o, d, kRayEpsilon, CUDART_INF);
                         if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
+                        if (ANY && !LIST) any_begin<COUNT>(w, sc, lc);
                         lc.rays++;
                     } else {
                         for (int b = static_cast<int>(nb) - 1; b >= 0; --b) {
@@ -1207,6 +1394,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
                     const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
                     walker_start(w, sc, tune, mk(r0.x, r0.y, r1.x), mk(r1.y, r2.x, r2.y), r3.x, r3.y);
                     if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
+                    if (ANY && !LIST) any_begin<COUNT>(w, sc, lc);
                     if (OUT == OUT_TAIL) pst = ta.q.state[ta.bounce & 1u][i];
                     lc.rays++;
                 }
@@ -1225,7 +1413,10 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
             for (;;) {
 #pragma unroll
                 for (int rep = 0; rep < 2; ++rep)
-                    if ((w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
+                    if ((w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32) {
+                        if (ANY && w.any) walker_step_any<COUNT>(w, sc, lc, my_stack2, stride);
+                        else walker_step_wide<COUNT>(w, sc, lc, my_stack, ANY ? 2u * stride : stride);
+                    }
                 const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32);
                 if (walking == 0u) break;
                 const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
@@ -1239,7 +1430,15 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
         }
 
         // ---- leaves: exact gate + primitive test for the parked lanes --------------------------------
-        if (w.prim != kNoPrim) walker_leaf<COUNT>(w, sc, lc);
+        if (w.prim != kNoPrim) {
+            if (ANY && w.any) {
+                any_test<COUNT>(w, sc, lc, w.prim);
+                w.prim = w.prim2;
+                w.prim2 = kNoPrim;
+            } else {
+                walker_leaf<COUNT>(w, sc, lc);
+            }
+        }
     }
 
     flush_counters<COUNT>(counters, lc);
@@ -1330,6 +1529,7 @@ __global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 
 constexpr int kPipeDepth = 3;
+constexpr size_t kAnyOrderAutoLeaves = 0;  // every eligible scene takes the any-order walk by default (measured faster from the 4,969-leaf bunny up)
 constexpr unsigned kQueueSlots = 64;
 static size_t chunk_rays() {  // rays per pipeline stage: 2^18 (16 MiB of rays) unless RTP_CHUNK_LOG2 says otherwise (tuning runs)
     static const size_t v = [] { const char* e = std::getenv("RTP_CHUNK_LOG2"); const int l = e ? std::atoi(e) : 18; return size_t(1) << std::max(10, std::min(24, l)); }();
@@ -1356,6 +1556,7 @@ struct DeviceScene {
     WorkQueue* queues = nullptr;       // kQueueSlots self-rearming work queues, handed out round-robin per launch
     std::atomic<unsigned> queue_seq{0};  // launches from several host threads never share a slot unless > kQueueSlots are in flight
     int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
+    bool any_order = false;            // eligible rays take the any-order walk (RTP_TRAVERSAL, kAnyOrderAutoLeaves)
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
     Tuning tune{16, 8, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
@@ -1427,6 +1628,16 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     // one stack word per tree level and thread; a tree deeper than 96 levels (degenerate geometry) does not get the f32 walk
     // at all (view.f32_culling below), so its launches carry no stack
     ds->stack_bytes = static_cast<size_t>(flat.wide_depth <= 96 ? std::max<uint32_t>(flat.wide_depth, 1u) : 1u) * 128 * sizeof(uint32_t);
+    {
+        // RTP_TRAVERSAL=any | inorder overrides the choice
+        const char* tv = std::getenv("RTP_TRAVERSAL");
+        const bool f32_ok = flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96;
+        bool want = flat.prims.size() >= kAnyOrderAutoLeaves;
+        if (tv && std::string(tv) == "any") want = true;
+        if (tv && std::string(tv) == "inorder") want = false;
+        if (const char* v = std::getenv("RTP_F32_CULLING")) if (std::atoi(v) == 0) want = false;
+        ds->any_order = want && flat.any_ok && f32_ok;
+    }
     if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.materials, &ds->materials, &ds->bytes)) != RTP_OK) return bail(rc);
@@ -1447,12 +1658,24 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     if (e == cudaSuccess) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, ds->device);
-        int per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, ds->stack_bytes);
+        int per_sm = 0, tail_per_sm = 0;
+        if (ds->any_order) {
+            // any-order lanes postpone up to three siblings per level, each with its entry distance: (3 x depth + 1) x 8 B per thread
+            ds->stack_bytes = (3 * static_cast<size_t>(std::max<uint32_t>(flat.wide_depth, 1u)) + 1) * 128 * sizeof(uint2);
+            if (ds->stack_bytes > 48 * 1024) {
+#define RTP_SMEM_OPT_IN(C, O) if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_persistent_kernel<C, O, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ds->stack_bytes))
+                RTP_SMEM_OPT_IN(false, OUT_HIT); RTP_SMEM_OPT_IN(true, OUT_HIT); RTP_SMEM_OPT_IN(false, OUT_FULL); RTP_SMEM_OPT_IN(true, OUT_FULL);
+                RTP_SMEM_OPT_IN(false, OUT_WAVE); RTP_SMEM_OPT_IN(true, OUT_WAVE); RTP_SMEM_OPT_IN(false, OUT_TAIL); RTP_SMEM_OPT_IN(true, OUT_TAIL);
+#undef RTP_SMEM_OPT_IN
+            }
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, true>, 128, ds->stack_bytes);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, true>, 128, ds->stack_bytes);
+        } else {
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, false>, 128, ds->stack_bytes);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, false>, 128, ds->stack_bytes);
+        }
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 3;
-        int tail_per_sm = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false>, 128, ds->stack_bytes);
         ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (const char* v = std::getenv("RTP_TAIL_THRESHOLD")) ds->tail_threshold = static_cast<uint32_t>(std::max(0l, std::atol(v)));
         if (const char* v = std::getenv("RTP_TAIL_OFFER")) ds->tail_offer = std::atoi(v) != 0;
@@ -1482,6 +1705,10 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     v.n_prims = static_cast<uint32_t>(flat.prims.size());
     v.root_kind = flat.root_kind;
     v.bg_kind = flat.background.kind; v.bg_texture = flat.background.texture;
+    v.any_order = ds->any_order ? 1u : 0u;
+    v.n_big = flat.n_big;
+    std::memcpy(v.big, flat.big, sizeof v.big);
+    v.any_E = flat.any_E; v.any_A = flat.any_A;
     std::memcpy(v.bg_rgb, flat.background.rgb, sizeof v.bg_rgb);
     *out = ds;
     return RTP_OK;
@@ -1528,11 +1755,13 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         WorkQueue* wq = ds->queues + (ds->queue_seq.fetch_add(1u) % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
         const TailArgs ta = tail ? *tail : TailArgs{};
-#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta)
+        const bool any = ds->any_order && !list;
+#define RTP_LAUNCH_PERSISTENT(C, O, L, A) trace_persistent_kernel<C, O, L, A><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta)
 #define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
     do {                                                                                             \
-        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true); else RTP_LAUNCH_PERSISTENT(false, O, true); }     \
-        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false); else RTP_LAUNCH_PERSISTENT(false, O, false); }        \
+        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true, false); else RTP_LAUNCH_PERSISTENT(false, O, true, false); }     \
+        else if (any) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, true); else RTP_LAUNCH_PERSISTENT(false, O, false, true); } \
+        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, false); else RTP_LAUNCH_PERSISTENT(false, O, false, false); }        \
     } while (0)
         if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
         else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);
@@ -1593,7 +1822,7 @@ static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hit
         float ms = 0.f;
         RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
         std::memset(stats, 0, sizeof *stats);
-        stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations;
+        stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
         stats->device_ms = ms; stats->kernel_launches = launches;
     }
     return RTP_OK;
@@ -1742,7 +1971,7 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
         RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
         std::memset(stats, 0, sizeof *stats);
         stats->rays = c.rays; stats->paths = static_cast<uint64_t>(npix) * ns_total;
-        stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations;
+        stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
         stats->device_ms = ms; stats->kernel_launches = launches;
     }
     return RTP_OK;
@@ -1906,7 +2135,7 @@ int rtp_trace_closest_device_counted(rtp_scene* scene, const rtp_ray* d_rays, si
     float ms = 0.f;
     RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
     std::memset(stats, 0, sizeof *stats);
-    stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations;
+    stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
     stats->device_ms = ms; stats->kernel_launches = 1;
     return RTP_OK;
 }

@@ -346,6 +346,66 @@ static void build_wide(FlatScene* out) {
     }
 }
 
+// Scene-side preparation of the any-order walk (rtp_device.cu walker_step_any). Distance culling is exact only
+// with a bound on how far a triangle's computed t (hittable.rs:85-95) can fall below the computed slab entry of its own box;
+// that bound grows with the triangle's extent, so outsized triangles and all spheres (whose roots cancel catastrophically,
+// hittable.rs:44-47) are taken out of the culled set: they are the "big" primitives, tested for every ray before the walk.
+// More than kMaxBig of them, or a tree too deep for the shared-memory stack, and the scene keeps the in-order walk.
+static void prepare_any_order(FlatScene* out) {
+    out->any_ok = false;
+    out->n_big = 0;
+    const size_t n = out->prims.size();
+    if (!out->boxes_finite || n == 0 || out->root_kind != RTP_ROOT_BVH || out->wide_depth > 28) return;
+    std::vector<uint8_t> kind(n, 0);
+    for (const DNode& nd : out->nodes)
+        if (nd.prim != kNoPrim) kind[nd.prim] = static_cast<uint8_t>(nd.kind);
+    auto extent = [&](size_t s) {
+        const DPrim& p = out->prims[s];
+        return std::fmax(p.bmax[0] - p.bmin[0], std::fmax(p.bmax[1] - p.bmin[1], p.bmax[2] - p.bmin[2]));
+    };
+    std::vector<double> ext;
+    ext.reserve(n);
+    for (size_t s = 0; s < n; ++s) {
+        if (kind[s] == RTP_HITTABLE_SPHERE) {
+            if (out->n_big == kMaxBig) return;
+            out->big[out->n_big++] = static_cast<uint32_t>(s) | (static_cast<uint32_t>(RTP_HITTABLE_SPHERE) << 31);
+        } else {
+            ext.push_back(extent(s));
+        }
+    }
+    std::vector<uint8_t> is_big(n, 0);
+    for (uint32_t b = 0; b < out->n_big; ++b) is_big[out->big[b] & 0x7FFFFFFFu] = 1;
+    if (!ext.empty()) {
+        std::vector<double> tmp = ext;
+        std::nth_element(tmp.begin(), tmp.begin() + tmp.size() / 2, tmp.end());
+        const double cap = 16.0 * tmp[tmp.size() / 2];
+        // the largest triangles above the cap, as many as fit
+        std::vector<std::pair<double, uint32_t>> over;
+        for (size_t s = 0; s < n; ++s)
+            if (kind[s] != RTP_HITTABLE_SPHERE && extent(s) > cap) over.push_back({extent(s), static_cast<uint32_t>(s)});
+        std::sort(over.begin(), over.end(), [](const auto& a, const auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+        for (size_t k = 0; k < over.size() && out->n_big < kMaxBig; ++k) {
+            out->big[out->n_big++] = over[k].second | (static_cast<uint32_t>(RTP_HITTABLE_TRIANGLE) << 31);
+            is_big[over[k].second] = 1;
+        }
+    }
+    double E = 0.0, A = 0.0;
+    for (size_t s = 0; s < n; ++s) {
+        if (is_big[s]) continue;
+        const DPrim& p = out->prims[s];
+        E = std::fmax(E, extent(s));
+        for (int k = 0; k < 3; ++k) A = std::fmax(A, std::fmax(std::fabs(p.bmin[k]), std::fabs(p.bmax[k])));
+    }
+    out->any_E = E * (1.0 + 1e-12);
+    out->any_A = A * (1.0 + 1e-12);
+    for (DWide& w : out->wide) {
+        w.big_mask = 0;
+        for (int k = 0; k < 4; ++k)
+            if (w.child[k] != kWideEmpty && (w.child[k] & kWideLeaf) && is_big[w.child[k] & 0x3FFFFFFFu]) w.big_mask |= 1u << k;
+    }
+    out->any_ok = true;
+}
+
 static bool emit_ok(const rtp_emit& e, uint32_t n_textures) {
     if (e.kind > RTP_EMIT_SKY_SPHERE) return false;
     return e.kind != RTP_EMIT_SKY_SPHERE || e.texture < n_textures;
@@ -559,6 +619,8 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
             if (nd.prim != kNoPrim) nd.kind = d->hittables[items[nd.prim].id].kind;
         build_wide(out);
         lap("4-wide collapse");
+        prepare_any_order(out);
+        lap("any-order walk tables");
     } else {
         // a List root is traversed as a flat run of leaves without slab tests; nodes carry only the kind
         out->nodes.assign(n ? n : 1, DNode{});

@@ -60,7 +60,8 @@ constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
 struct alignas(128) DWide {  // 128 B = one L1/L2 line
     float plane[3][2][4];    // [axis][0 = min, 1 = max][child]
     uint32_t child[4];
-    uint32_t _pad[4];
+    uint32_t big_mask;       // bit k: child k is a leaf holding one of the scene's "big" primitives (any-order walk: tested up front)
+    uint32_t _pad[3];
 };
 static_assert(sizeof(DWide) == 128, "DWide must be 128 bytes");
 
@@ -106,7 +107,15 @@ struct DSceneView {  // passed by value to kernels
     uint32_t bg_texture;
     uint32_t f32_culling;  // 1: scene magnitudes allow the f32 conservative slab test
     double bg_rgb[3];
+    // any-order walk: front-to-back traversal with distance culling, exact because every leaf that can matter is
+    // still tested and the rare ray whose answer could depend on the reference's visiting order is re-walked in order
+    uint32_t any_order;    // 1: eligible rays of this scene use it
+    uint32_t n_big;        // primitives tested before the walk (all spheres, outsized triangles), at most kMaxBig
+    uint32_t big[8];       // slot | kind << 31
+    double any_E;          // largest box extent of a triangle that is not big
+    double any_A;          // largest |coordinate| of such a triangle
 };
+constexpr uint32_t kMaxBig = 8;
 
 // ---------------------------------------------------------------------------------------------
 // Host-side flattened scene produced by rtp_host.cpp and uploaded by rtp_device.cu
@@ -126,6 +135,10 @@ struct FlatScene {
     uint32_t depth = 0;              // of the reference tree (bvh.rs), what rtp_scene_info reports
     uint32_t n_reference_nodes = 0;  // 2n-1
     uint32_t device_depth = 0;       // of the culling tree the kernels walk
+    bool any_ok = false;             // the any-order walk may be used on this scene (prepare_any_order, rtp_host.cpp)
+    uint32_t n_big = 0;
+    uint32_t big[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double any_E = 0.0, any_A = 0.0;
     double scene_mag = 0.0;    // largest |coordinate| of any node box
     bool boxes_finite = true;  // every box is finite and ordered (min <= max): precondition of the sign-selected slab test, of the
                                // f32 culling walk and of re-shaping the tree; otherwise the reference topology and the literal test are used
