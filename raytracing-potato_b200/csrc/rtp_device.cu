@@ -621,12 +621,6 @@ __device__ __forceinline__ void any_begin(Walker& w, const DSceneView& sc, Local
     w.any = true;
     w.T_win = w.h.t;
     w.A_min = CUDART_INF;
-    for (uint32_t b = 0; b < sc.n_big; ++b) {
-        // a big primitive whose own box the ray never enters fails the reference's leaf gate for every t_max (bvh.rs:96): skip it
-        const double* pb = sc.prims[sc.big[b] & 0x7FFFFFFFu].bmin;
-        if (COUNT) lc.leaf_gates++;
-        if (collide_fast(ldg2(pb), ldg2(pb + 2), ldg2(pb + 4), w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, CUDART_INF)) any_test<COUNT>(w, sc, lc, sc.big[b]);
-    }
 }
 
 __device__ __forceinline__ void any_park(Walker& w, uint32_t c) {
@@ -665,11 +659,14 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
     const uint32_t big = __ldg(reinterpret_cast<const uint32_t*>(np + 112u));
     const Ray32& r = w.r32;
     // key = entry distance (non-negative float: its bits order like the value) with the child index in the two low bits;
-    // children that are missed, beyond the window, empty or big get the largest key
+    // children that are missed, beyond the window or empty get the largest key. A child that holds a big primitive (big_mask)
+    // is exempt from the window - the slack bound does not cover what is inside - and gets key 0: visited first, never
+    // dropped when it is popped, so a big primitive is tested whenever the ray enters its box at all
 #define RTP_KEY(c, idx)                                                                                                        \
+    const bool g##c = ((big >> idx) & 1u) != 0u;                                                                                   \
     const float n##c = fmaxf(fmaxf(fmaf(nx4.c, r.ix, r.clx), fmaf(ny4.c, r.iy, r.cly)), fmaxf(fmaf(nz4.c, r.iz, r.clz), r.tmin_dn)); \
-    const float f##c = fminf(fminf(fmaf(fx4.c, r.ix, r.chx), fmaf(fy4.c, r.iy, r.chy)), fminf(fmaf(fz4.c, r.iz, r.chz), r.T_up));    \
-    const uint32_t k##c = (f##c >= n##c && !((big >> idx) & 1u)) ? ((__float_as_uint(n##c) & ~3u) | idx) : 0xFFFFFFFFu;
+    const float f##c = fminf(fminf(fmaf(fx4.c, r.ix, r.chx), fmaf(fy4.c, r.iy, r.chy)), fminf(fmaf(fz4.c, r.iz, r.chz), g##c ? CUDART_INF_F : r.T_up)); \
+    const uint32_t k##c = f##c >= n##c ? ((g##c ? 0u : (__float_as_uint(n##c) & ~3u)) | idx) : 0xFFFFFFFFu;
     RTP_KEY(x, 0u) RTP_KEY(y, 1u) RTP_KEY(z, 2u) RTP_KEY(w, 3u)
 #undef RTP_KEY
     if (COUNT) {
@@ -677,8 +674,8 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
         const double* b64 = sc.wide_boxes + static_cast<size_t>(w.next) * 24;
         const uint32_t keys[4] = {kx, ky, kz, kw};
         for (uint32_t k = 0; k < 4; ++k)  // a rejected child must fail the exact test with the window top as t_max
-            if (keys[k] == 0xFFFFFFFFu && !((big >> k) & 1u) && (&ch.x)[k] != kWideEmpty &&
-                collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), w.o, w.inv, w.tmin, w.T_win))
+            if (keys[k] == 0xFFFFFFFFu && (&ch.x)[k] != kWideEmpty &&
+                collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), w.o, w.inv, w.tmin, ((big >> k) & 1u) ? CUDART_INF : w.T_win))
                 lc.violations++;
     }
     // sorting network for four keys
@@ -1676,6 +1673,9 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         }
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 3;
+        if (const char* v = std::getenv("RTP_BUILD_TIMING")) if (std::atoi(v) != 0)
+            std::fprintf(stderr, "[rtp build] 4-wide tree depth %u, %s walk (%u big primitives), %zu B of stack per block, %d traversal blocks per SM\n", flat.wide_depth,
+                         ds->any_order ? "any-order" : "in-order", flat.n_big, ds->stack_bytes, per_sm);
         ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (const char* v = std::getenv("RTP_TAIL_THRESHOLD")) ds->tail_threshold = static_cast<uint32_t>(std::max(0l, std::atol(v)));
         if (const char* v = std::getenv("RTP_TAIL_OFFER")) ds->tail_offer = std::atoi(v) != 0;

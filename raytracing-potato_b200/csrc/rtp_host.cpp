@@ -398,10 +398,18 @@ static void prepare_any_order(FlatScene* out) {
     }
     out->any_E = E * (1.0 + 1e-12);
     out->any_A = A * (1.0 + 1e-12);
-    for (DWide& w : out->wide) {
+    // children are appended after their parents (build_wide), so one backward sweep propagates "contains a big primitive" upwards
+    std::vector<uint8_t> has_big(out->wide.size(), 0);
+    for (size_t i = out->wide.size(); i-- > 0;) {
+        DWide& w = out->wide[i];
         w.big_mask = 0;
-        for (int k = 0; k < 4; ++k)
-            if (w.child[k] != kWideEmpty && (w.child[k] & kWideLeaf) && is_big[w.child[k] & 0x3FFFFFFFu]) w.big_mask |= 1u << k;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t c = w.child[k];
+            if (c == kWideEmpty) continue;
+            const bool big = (c & kWideLeaf) ? is_big[c & 0x3FFFFFFFu] != 0 : (c > i ? has_big[c] != 0 : true);
+            if (big) w.big_mask |= 1u << k;
+        }
+        has_big[i] = w.big_mask != 0;
     }
     out->any_ok = true;
 }

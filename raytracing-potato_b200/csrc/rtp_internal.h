@@ -60,7 +60,7 @@ constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
 struct alignas(128) DWide {  // 128 B = one L1/L2 line
     float plane[3][2][4];    // [axis][0 = min, 1 = max][child]
     uint32_t child[4];
-    uint32_t big_mask;       // bit k: child k is a leaf holding one of the scene's "big" primitives (any-order walk: tested up front)
+    uint32_t big_mask;       // bit k: child k is, or contains, one of the scene's "big" primitives (any-order walk: exempt from distance culling)
     uint32_t _pad[3];
 };
 static_assert(sizeof(DWide) == 128, "DWide must be 128 bytes");
@@ -110,7 +110,7 @@ struct DSceneView {  // passed by value to kernels
     // any-order walk: front-to-back traversal with distance culling, exact because every leaf that can matter is
     // still tested and the rare ray whose answer could depend on the reference's visiting order is re-walked in order
     uint32_t any_order;    // 1: eligible rays of this scene use it
-    uint32_t n_big;        // primitives tested before the walk (all spheres, outsized triangles), at most kMaxBig
+    uint32_t n_big;        // primitives exempt from distance culling (all spheres, outsized triangles), at most kMaxBig
     uint32_t big[8];       // slot | kind << 31
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
