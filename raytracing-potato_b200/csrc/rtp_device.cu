@@ -436,12 +436,6 @@ struct Tuning {
 //   entries in shared memory holds the ancestors that still have pending children.
 //   Other lanes (non-finite or axis-parallel rays, huge coordinates, List roots) walk the exact f64 pre-order tree with
 //   `next` as the pre-order index (bvh.rs:93-119 literally).
-#ifndef RTP_ANY_BLOCKS
-#define RTP_ANY_BLOCKS 5
-#endif
-#ifndef RTP_ANY_POPS
-#define RTP_ANY_POPS 1
-#endif
 constexpr uint32_t kEnd = 0xFFFFFFFFu;   // `next`: the walk is over
 constexpr uint32_t kNone = 0xFFFFFFFEu;  // `next`: no node to visit, take the next pending child
 struct Walker {
@@ -574,8 +568,9 @@ __device__ __forceinline__ bool any_slack(const Walker& w, const DSceneView& sc,
     const double e_uv = K * (6.0 * P * E * D + 6.06 * D * E * E) + 3.0 * u;
     if (!(kappa <= 0.25) || !(e_uv <= 0.01)) return false;
     const double eta = (4.0 * e_uv + 5.0 * u) * E;
-    const double s0 = 4.0 * ((eta + u * P) * I * (1.0 + u) + K * 6.0 * P * E * E / (1.0 - kappa) + 3.0 * u * fabs(w.tmin));
-    const double s1 = 4.0 * ((K * 6.0 * D * E * E + 5.0 * u) / (1.0 - kappa));
+    // 1 / (1 - kappa) <= 4/3 for kappa <= 1/4: no divide on the per-ray path; the factor 4 in front absorbs the second-order terms
+    const double s0 = 4.0 * ((eta + u * P) * I * (1.0 + u) + (K * 6.0 * P * E * E) * (4.0 / 3.0 + 1e-9) + 3.0 * u * fabs(w.tmin));
+    const double s1 = 4.0 * ((K * 6.0 * D * E * E + 5.0 * u) * (4.0 / 3.0 + 1e-9));
     s0f = __double2float_ru(s0); s1f = __double2float_ru(s1);
     return s0f <= 3.0e38f && s1f <= 3.0e38f;
 }
@@ -623,11 +618,14 @@ __device__ __forceinline__ void any_begin(Walker& w, const DSceneView& sc, Local
     w.A_min = CUDART_INF;
 }
 
-__device__ __forceinline__ void any_park(Walker& w, uint32_t c) {
+// hand a child word to the lane: a leaf is parked (oldest pending leaf first), an internal child becomes the node to visit; selects only
+__device__ __forceinline__ void any_take(Walker& w, uint32_t c) {
+    const bool is_leaf = (c & kWideLeaf) != 0u;
     const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
     const bool first = w.prim == kNoPrim;
-    w.prim2 = first ? w.prim2 : leaf;
-    w.prim = first ? leaf : w.prim;
+    w.prim2 = (is_leaf & !first) ? leaf : w.prim2;
+    w.prim = (is_leaf & first) ? leaf : w.prim;
+    w.next = is_leaf ? kNone : c;
 }
 
 // One step of a lane in any-order mode: take a node (the pending one, else the nearest postponed entry that survives the
@@ -636,17 +634,12 @@ __device__ __forceinline__ void any_park(Walker& w, uint32_t c) {
 template <bool COUNT>
 __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc, LocalCounters& lc, uint2* __restrict__ stack, uint32_t stride) {
     if (w.next == kNone) {
-        uint2 e;
-#pragma unroll 1
-        for (int tries = 0;; ++tries) {
-            if (w.sp == 0u) { w.next = kEnd; return; }
-            w.sp -= 1u;
-            e = stack[w.sp * stride];
-            if (__uint_as_float(e.y) <= w.r32.T_up) break;  // else: the window shrank since this entry was postponed
-            if (tries + 1 == RTP_ANY_POPS) return;
-        }
-        if (e.x & kWideLeaf) { any_park(w, e.x); return; }
-        w.next = e.x;
+        if (w.sp == 0u) { w.next = kEnd; return; }
+        w.sp -= 1u;
+        const uint2 e = stack[w.sp * stride];
+        if (__uint_as_float(e.y) > w.r32.T_up) return;  // the window shrank since this entry was postponed
+        any_take(w, e.x);
+        if (w.next == kNone) return;
     }
     const char* np = reinterpret_cast<const char*>(sc.wide + w.next);
     const float4 nx4 = __ldg(reinterpret_cast<const float4*>(np + w.onx));
@@ -678,10 +671,15 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
                 collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), w.o, w.inv, w.tmin, ((big >> k) & 1u) ? CUDART_INF : w.T_win))
                 lc.violations++;
     }
-    // sorting network for four keys
+    // sorting network for four keys (measured: visiting the postponed children nearest-first beats index order everywhere)
     const uint32_t a0 = min(kx, ky), a1 = max(kx, ky), b0 = min(kz, kw), b1 = max(kz, kw);
     const uint32_t s0 = min(a0, b0), m0 = max(a0, b0), m1 = min(a1, b1), s3 = max(a1, b1);
     const uint32_t s1 = min(m0, m1), s2 = max(m0, m1);
+    if (w.sp + 3u > sc.any_cap) {
+        // no room to postpone three children (the stack holds any_cap entries per lane): give the ray to the in-order walk
+        w.next = kEnd; w.prim = kNoPrim; w.prim2 = kNoPrim; w.A_min = -CUDART_INF;
+        return;
+    }
 #define RTP_SEL(k) __funnelshift_rc(__funnelshift_rc(ch.x, ch.y, ((k) & 1u) << 5), __funnelshift_rc(ch.z, ch.w, ((k) & 1u) << 5), ((k) & 2u) << 4)
 #define RTP_PUSH(s)                                                                       \
     if ((s) != 0xFFFFFFFFu) {                                                             \
@@ -691,11 +689,7 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
     RTP_PUSH(s3) RTP_PUSH(s2) RTP_PUSH(s1)
 #undef RTP_PUSH
     w.next = kNone;
-    if (s0 != 0xFFFFFFFFu) {
-        const uint32_t c = RTP_SEL(s0);
-        if (c & kWideLeaf) any_park(w, c);
-        else w.next = c;
-    }
+    if (s0 != 0xFFFFFFFFu) any_take(w, RTP_SEL(s0));
 #undef RTP_SEL
 }
 
@@ -1261,10 +1255,11 @@ struct TailArgs {
 };
 
 constexpr int kTraceBlocksPerSM = 6;
-constexpr int kTraceBlocksPerSMAny = RTP_ANY_BLOCKS;  // the any-order variant carries both walkers' state
 
-template <bool COUNT, int OUT, bool LIST, bool ANY>
-__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY ? kTraceBlocksPerSMAny : kTraceBlocksPerSM)) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+// ANY: 0 = every lane walks in the reference's order; 1, 2 = eligible lanes take the any-order walk, built for 5 resident blocks per
+// SM (96 registers, a few spills: best while the scene is cache-resident) or 4 (120 registers, none: best for scenes in HBM)
+template <bool COUNT, int OUT, bool LIST, int ANY>
+__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (ANY == 1 ? 5 : kTraceBlocksPerSM))) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev,
                                                                   TailArgs ta) {
     extern __shared__ __align__(16) uint32_t wide_stack[];  // [level][thread]; any-order lanes: [entry][thread] of uint2
@@ -1526,6 +1521,7 @@ __global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 
 constexpr int kPipeDepth = 3;
+constexpr size_t kAnyOrderBigScene = 262144;  // leaves from which the 4-blocks-per-SM variant is used
 constexpr size_t kAnyOrderAutoLeaves = 0;  // every eligible scene takes the any-order walk by default (measured faster from the 4,969-leaf bunny up)
 constexpr unsigned kQueueSlots = 64;
 static size_t chunk_rays() {  // rays per pipeline stage: 2^18 (16 MiB of rays) unless RTP_CHUNK_LOG2 says otherwise (tuning runs)
@@ -1553,7 +1549,8 @@ struct DeviceScene {
     WorkQueue* queues = nullptr;       // kQueueSlots self-rearming work queues, handed out round-robin per launch
     std::atomic<unsigned> queue_seq{0};  // launches from several host threads never share a slot unless > kQueueSlots are in flight
     int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
-    bool any_order = false;            // eligible rays take the any-order walk (RTP_TRAVERSAL, kAnyOrderAutoLeaves)
+    int any_order = 0;                 // 1, 2: eligible rays take the any-order walk (RTP_TRAVERSAL), kernel variant ANY = 1 or 2
+    uint32_t any_cap = 0;              // any-order stack entries per lane
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
     Tuning tune{16, 8, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
@@ -1633,7 +1630,9 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         if (tv && std::string(tv) == "any") want = true;
         if (tv && std::string(tv) == "inorder") want = false;
         if (const char* v = std::getenv("RTP_F32_CULLING")) if (std::atoi(v) == 0) want = false;
-        ds->any_order = want && flat.any_ok && f32_ok;
+        // scenes that live in HBM rather than in the caches run the spill-free 4-blocks-per-SM build of the kernel
+        ds->any_order = (want && flat.any_ok && f32_ok) ? (flat.prims.size() >= kAnyOrderBigScene ? 2 : 1) : 0;
+        if (const char* v = std::getenv("RTP_ANY_VARIANT")) if (ds->any_order) ds->any_order = std::atoi(v) == 2 ? 2 : 1;
     }
     if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
@@ -1657,19 +1656,22 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         e = cudaGetDeviceProperties(&prop, ds->device);
         int per_sm = 0, tail_per_sm = 0;
         if (ds->any_order) {
-            // any-order lanes postpone up to three siblings per level, each with its entry distance: (3 x depth + 1) x 8 B per thread
-            ds->stack_bytes = (3 * static_cast<size_t>(std::max<uint32_t>(flat.wide_depth, 1u)) + 1) * 128 * sizeof(uint2);
-            if (ds->stack_bytes > 48 * 1024) {
-#define RTP_SMEM_OPT_IN(C, O) if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_persistent_kernel<C, O, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ds->stack_bytes))
-                RTP_SMEM_OPT_IN(false, OUT_HIT); RTP_SMEM_OPT_IN(true, OUT_HIT); RTP_SMEM_OPT_IN(false, OUT_FULL); RTP_SMEM_OPT_IN(true, OUT_FULL);
-                RTP_SMEM_OPT_IN(false, OUT_WAVE); RTP_SMEM_OPT_IN(true, OUT_WAVE); RTP_SMEM_OPT_IN(false, OUT_TAIL); RTP_SMEM_OPT_IN(true, OUT_TAIL);
-#undef RTP_SMEM_OPT_IN
+            // any-order lanes postpone up to three siblings per level, each with its entry distance: at most 3 x depth + 1 entries of
+            // 8 B per lane, capped at 32 (a lane that would need more hands its ray to the in-order walk, whose one-word entries
+            // live in the same column: at least `depth` slots)
+            ds->any_cap = std::max<uint32_t>(flat.wide_depth, std::min<uint32_t>(3u * flat.wide_depth + 1u, 32u));
+            if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = std::max<uint32_t>(flat.wide_depth, static_cast<uint32_t>(std::max(1, std::min(48, std::atoi(v)))));  // tests
+            ds->stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
+            if (ds->any_order == 2) {
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 2>, 128, ds->stack_bytes);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 2>, 128, ds->stack_bytes);
+            } else {
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 1>, 128, ds->stack_bytes);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 1>, 128, ds->stack_bytes);
             }
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, true>, 128, ds->stack_bytes);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, true>, 128, ds->stack_bytes);
         } else {
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, false>, 128, ds->stack_bytes);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, false>, 128, ds->stack_bytes);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 0>, 128, ds->stack_bytes);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 0>, 128, ds->stack_bytes);
         }
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 3;
@@ -1706,6 +1708,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     v.root_kind = flat.root_kind;
     v.bg_kind = flat.background.kind; v.bg_texture = flat.background.texture;
     v.any_order = ds->any_order ? 1u : 0u;
+    v.any_cap = ds->any_cap;
     v.n_big = flat.n_big;
     std::memcpy(v.big, flat.big, sizeof v.big);
     v.any_E = flat.any_E; v.any_A = flat.any_A;
@@ -1755,13 +1758,14 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         WorkQueue* wq = ds->queues + (ds->queue_seq.fetch_add(1u) % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
         const TailArgs ta = tail ? *tail : TailArgs{};
-        const bool any = ds->any_order && !list;
+        const int any = list ? 0 : ds->any_order;
 #define RTP_LAUNCH_PERSISTENT(C, O, L, A) trace_persistent_kernel<C, O, L, A><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta)
 #define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
     do {                                                                                             \
-        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true, false); else RTP_LAUNCH_PERSISTENT(false, O, true, false); }     \
-        else if (any) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, true); else RTP_LAUNCH_PERSISTENT(false, O, false, true); } \
-        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, false); else RTP_LAUNCH_PERSISTENT(false, O, false, false); }        \
+        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true, 0); else RTP_LAUNCH_PERSISTENT(false, O, true, 0); }     \
+        else if (any == 2) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 2); else RTP_LAUNCH_PERSISTENT(false, O, false, 2); } \
+        else if (any == 1) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 1); else RTP_LAUNCH_PERSISTENT(false, O, false, 1); } \
+        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 0); else RTP_LAUNCH_PERSISTENT(false, O, false, 0); }        \
     } while (0)
         if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
         else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);

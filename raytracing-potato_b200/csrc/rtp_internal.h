@@ -110,8 +110,9 @@ struct DSceneView {  // passed by value to kernels
     // any-order walk: front-to-back traversal with distance culling, exact because every leaf that can matter is
     // still tested and the rare ray whose answer could depend on the reference's visiting order is re-walked in order
     uint32_t any_order;    // 1: eligible rays of this scene use it
+    uint32_t any_cap;      // entries of the per-lane any-order stack
     uint32_t n_big;        // primitives exempt from distance culling (all spheres, outsized triangles), at most kMaxBig
-    uint32_t big[8];       // slot | kind << 31
+    uint32_t big[7];       // slot | kind << 31 (first seven; informational)
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
 };

@@ -844,3 +844,37 @@ def test_any_order_walk_renders_match_oracle(gpu, monkeypatch, name, w, h, spp):
     ig2, _, _ = g.render(w, h, spp, seed=3, tile=(32, 16, 32, 32))  # a 32x32 tile runs as one tail-mode launch
     assert np.array_equal(ig2[16:48, 32:64], ig[16:48, 32:64])
     g.close(); o.close()
+
+
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_any_order_stack_overflow_hands_the_ray_to_the_in_order_walk(gpu, monkeypatch, variant):
+    """the any-order stack is capped per lane; a lane that cannot postpone three more children gives its ray to the in-order
+    walk. With the cap forced down to the tree depth most incoherent rays overflow: same bits, many re-walks. Both builds
+    of the kernel (5 and 4 resident blocks per SM)."""
+    import torch
+
+    monkeypatch.setenv("RTP_TRAVERSAL", "any")
+    monkeypatch.setenv("RTP_ANY_VARIANT", variant)
+    sc = scenes.bunny_lambert()
+    rays = _mixed_rays(sc)
+    o = oracle.Scene(sc)
+    want = o.hit(rays)
+    d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((len(rays), 2), dtype=torch.float64, device="cuda")
+    for cap, some in (("1", True), ("12", None), ("48", False)):
+        monkeypatch.setenv("RTP_ANY_CAP", cap)
+        g = api.Scene(sc)
+        st = g.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+        assert_hits_equal_bits(d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1), want)
+        assert_hits_equal_bits(g.hit(rays), want)
+        assert st.conservative_violations == 0
+        if some is True:
+            assert st.order_rewalks > 0, st.order_rewalks
+        if some is False:
+            assert st.order_rewalks <= len(rays) // 1000, st.order_rewalks
+        ig, fg, sg = g.render(64, 48, 2, seed=8)
+        io, fo, so = o.render(64, 48, 2, seed=8)
+        rep = image_report(ig, io)
+        assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+        g.close()
+    o.close()
