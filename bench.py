@@ -313,7 +313,7 @@ def main():
     # f64 work of the reference algorithm per launch: 24 ops per slab test, 75 per triangle test, 20 per sphere test
     f64_ops = 24 * cst.leaf_gates + 75 * cst.triangle_tests + 20 * cst.sphere_tests  # inner nodes are culled in f32
     fp64_peak = 148 * 64 * sm_hz  # 64 FP64 lanes per SM
-    scene_bytes = 128 * cst.node_visits + 128 * cst.leaf_gates  # one 128 B DWide per node visit, one 128 B DPrim per leaf
+    scene_bytes = 128 * cst.node_visits + 128 * (cst.triangle_tests + cst.sphere_tests)  # one 128 B DWide per node visit, one 128 B DPrim per tested leaf
 
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -332,14 +332,14 @@ def main():
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": {
-            "kernel": "trace_persistent_kernel<COUNT=false, OUT_HIT, LIST=false>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "kernel": "trace_persistent_kernel<COUNT=false, OUT_HIT, LIST=false, ANY=1> (any-order walk, DESIGN.md 4b)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms,
             "note": "the bunny scene (0.9 MB of culling nodes + primitives) is cache-resident, so HBM carries only the 80 B/ray stream; the kernel is bound by instruction issue and L1 latency (profiles/): see issue/fp64 below",
             "fp64": {"ops_per_launch": f64_ops, "achieved_gops": f64_ops / (kernel_ms * 1e-3) / 1e9, "peak_gops": fp64_peak / 1e9,
                      "frac": f64_ops / (kernel_ms * 1e-3) / fp64_peak, "peak_source": "148 SM x 64 FP64 lanes x median SM clock during the run"},
             "l2": {"bytes_per_launch": scene_bytes, "achieved_gbs": scene_bytes / (kernel_ms * 1e-3) / 1e9},
             "l1_note": "scene bytes are served by L1/L2, not HBM",
-            "issue": {"note": "binding resource per ncu (profiles/r01_trace_fifo_c2.md): smsp__issue_active 60 % of peak at 20.0 of 32 lanes per instruction, 34 % warp occupancy (80 registers, 6 blocks of 128 per SM); HBM 7 % of peak"},
+            "issue": {"note": "binding resource per ncu (profiles/r01_trace_any_c2.md): smsp__issue_active 61 % of peak at 22.7 of 32 lanes per instruction, 29 % warp occupancy (96 registers, 5 blocks of 128 per SM), L1 hit rate 69 %; HBM 7 % of peak"},
             "per_ray": {"node_visits": cst.node_visits / N_RAYS, "leaf_gates": cst.leaf_gates / N_RAYS, "triangle_tests": cst.triangle_tests / N_RAYS, "sphere_tests": cst.sphere_tests / N_RAYS,
                         "conservative_violations": int(cst.conservative_violations)},
         },
