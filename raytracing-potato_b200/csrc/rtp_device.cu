@@ -559,19 +559,24 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
 
 // per-ray slack coefficients; false: the ray is not eligible (bounds not self-consistent, or not finite)
 __device__ __forceinline__ bool any_slack(const Walker& w, const DSceneView& sc, float& s0f, float& s1f) {
-    const double u = 0x1.0p-53, K = 8.0 * u * 1e7;  // |det| >= 1e-7 (hittable.rs:80), 8u: rounding of a 6-term sum of products
-    const double P = fmax(fmax(fabs(w.o.x), fabs(w.o.y)), fabs(w.o.z)) + sc.any_A;
-    const double D = fmax(fmax(fabs(w.d.x), fabs(w.d.y)), fabs(w.d.z));
-    const double I = fmax(fmax(fabs(w.inv.x), fabs(w.inv.y)), fabs(w.inv.z));
-    const double E = sc.any_E;
-    const double kappa = K * 6.0 * D * E * E;
-    const double e_uv = K * (6.0 * P * E * D + 6.06 * D * E * E) + 3.0 * u;
-    if (!(kappa <= 0.25) || !(e_uv <= 0.01)) return false;
-    const double eta = (4.0 * e_uv + 5.0 * u) * E;
+    // evaluated in f32 with every operation rounded up (all quantities are non-negative), so the result is an upper bound of
+    // the real-number expression in DESIGN.md 4b; an overflow to +inf makes the ray ineligible
+    const float u = 0x1.0p-53f, K = 8.9e-9f;  // K >= 8 u 1e7: |det| >= 1e-7 (hittable.rs:80), 8u: rounding of a 6-term sum of products
+    const float P = __fadd_ru(__double2float_ru(fmax(fmax(fabs(w.o.x), fabs(w.o.y)), fabs(w.o.z))), sc.any_Af);
+    const float D = __double2float_ru(fmax(fmax(fabs(w.d.x), fabs(w.d.y)), fabs(w.d.z)));
+    const float I = __double2float_ru(fmax(fmax(fabs(w.inv.x), fabs(w.inv.y)), fabs(w.inv.z)));
+    const float E = sc.any_Ef;
+    const float E2 = __fmul_ru(E, E), DE2 = __fmul_ru(D, E2), PE = __fmul_ru(P, E);
+    const float kappa = __fmul_ru(__fmul_ru(K, 6.0f), DE2);
+    const float e_uv = __fadd_ru(__fmul_ru(K, __fadd_ru(__fmul_ru(6.0f, __fmul_ru(PE, D)), __fmul_ru(6.06f, DE2))), 3.0f * u);
+    if (!(kappa <= 0.25f) || !(e_uv <= 0.01f)) return false;
+    const float eta = __fmul_ru(__fadd_ru(__fmul_ru(4.0f, e_uv), 5.0f * u), E);
     // 1 / (1 - kappa) <= 4/3 for kappa <= 1/4: no divide on the per-ray path; the factor 4 in front absorbs the second-order terms
-    const double s0 = 4.0 * ((eta + u * P) * I * (1.0 + u) + (K * 6.0 * P * E * E) * (4.0 / 3.0 + 1e-9) + 3.0 * u * fabs(w.tmin));
-    const double s1 = 4.0 * ((K * 6.0 * D * E * E + 5.0 * u) * (4.0 / 3.0 + 1e-9));
-    s0f = __double2float_ru(s0); s1f = __double2float_ru(s1);
+    const float a0 = __fmul_ru(__fmul_ru(__fadd_ru(eta, __fmul_ru(u, P)), I), 1.0000002f);
+    const float a1 = __fmul_ru(__fmul_ru(__fmul_ru(K, 6.0f), __fmul_ru(PE, E)), 1.3333334f);
+    const float a2 = __fmul_ru(3.0f * u, __double2float_ru(fabs(w.tmin)));
+    s0f = __fmul_ru(4.0f, __fadd_ru(__fadd_ru(a0, a1), a2));
+    s1f = __fmul_ru(4.0f, __fmul_ru(__fadd_ru(__fmul_ru(__fmul_ru(K, 6.0f), DE2), 5.0f * u), 1.3333334f));
     return s0f <= 3.0e38f && s1f <= 3.0e38f;
 }
 
@@ -1404,7 +1409,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
             // ---- hot walk: f32-eligible lanes take up to two steps per vote -----------------------------------
             for (;;) {
 #pragma unroll
-                for (int rep = 0; rep < 2; ++rep)
+                for (int rep = 0; rep < 2; ++rep)  // measured: 3 or 4 steps per vote are slower in both walks
                     if ((w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32) {
                         if (ANY && w.any) walker_step_any<COUNT>(w, sc, lc, my_stack2, stride);
                         else walker_step_wide<COUNT>(w, sc, lc, my_stack, ANY ? 2u * stride : stride);
@@ -1712,6 +1717,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     v.n_big = flat.n_big;
     std::memcpy(v.big, flat.big, sizeof v.big);
     v.any_E = flat.any_E; v.any_A = flat.any_A;
+    v.any_Ef = std::nextafter(static_cast<float>(flat.any_E), std::numeric_limits<float>::infinity());  // >= any_E
+    v.any_Af = std::nextafter(static_cast<float>(flat.any_A), std::numeric_limits<float>::infinity());
     std::memcpy(v.bg_rgb, flat.background.rgb, sizeof v.bg_rgb);
     *out = ds;
     return RTP_OK;

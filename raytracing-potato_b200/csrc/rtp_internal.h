@@ -115,6 +115,7 @@ struct DSceneView {  // passed by value to kernels
     uint32_t big[7];       // slot | kind << 31 (first seven; informational)
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
+    float any_Ef, any_Af;  // the same, rounded up to f32
 };
 constexpr uint32_t kMaxBig = 8;
 
