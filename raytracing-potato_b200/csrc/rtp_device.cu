@@ -646,7 +646,7 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
         any_take(w, e.x);
         if (w.next == kNone) return;
     }
-    const char* np = reinterpret_cast<const char*>(sc.wide + w.next);
+    const char* np = reinterpret_cast<const char*>(sc.any_wide + w.next);
     const float4 nx4 = __ldg(reinterpret_cast<const float4*>(np + w.onx));
     const float4 fx4 = __ldg(reinterpret_cast<const float4*>(np + (16u - w.onx)));
     const float4 ny4 = __ldg(reinterpret_cast<const float4*>(np + 32u + w.ony));
@@ -669,7 +669,7 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
 #undef RTP_KEY
     if (COUNT) {
         lc.node_visits++;
-        const double* b64 = sc.wide_boxes + static_cast<size_t>(w.next) * 24;
+        const double* b64 = sc.any_boxes + static_cast<size_t>(w.next) * 24;
         const uint32_t keys[4] = {kx, ky, kz, kw};
         for (uint32_t k = 0; k < 4; ++k)  // a rejected child must fail the exact test with the window top as t_max
             if (keys[k] == 0xFFFFFFFFu && (&ch.x)[k] != kWideEmpty &&
@@ -1540,6 +1540,8 @@ struct DeviceScene {
     DNode* nodes = nullptr;
     DWide* wide = nullptr;
     double* wide_boxes = nullptr;
+    DWide* free_wide = nullptr;        // order-free culling tree of a big scene (any-order lanes), or nullptr
+    double* free_boxes = nullptr;
     size_t stack_bytes = 0;            // dynamic shared memory of the persistent kernels: wide_depth x 128 threads x 4 B
     DPrim* prims = nullptr;
     DAttr* attrs = nullptr;
@@ -1588,7 +1590,7 @@ static int upload(const std::vector<T>& v, T** out, uint64_t* bytes) {
 
 void device_scene_free(DeviceScene* ds) {
     if (!ds) return;
-    cudaFree(ds->nodes); cudaFree(ds->wide); cudaFree(ds->wide_boxes); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
+    cudaFree(ds->nodes); cudaFree(ds->wide); cudaFree(ds->wide_boxes); cudaFree(ds->free_wide); cudaFree(ds->free_boxes); cudaFree(ds->prims); cudaFree(ds->attrs); cudaFree(ds->materials); cudaFree(ds->textures);
     for (uint8_t* p : ds->images) cudaFree(p);
     cudaFree(ds->counters);
     cudaFree(ds->queues);
@@ -1624,6 +1626,10 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide, &ds->wide, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide_boxes, &ds->wide_boxes, &ds->bytes)) != RTP_OK) return bail(rc);
+    if (!flat.free_wide.empty()) {
+        if ((rc = upload(flat.free_wide, &ds->free_wide, &ds->bytes)) != RTP_OK) return bail(rc);
+        if ((rc = upload(flat.free_boxes, &ds->free_boxes, &ds->bytes)) != RTP_OK) return bail(rc);
+    }
     // one stack word per tree level and thread; a tree deeper than 96 levels (degenerate geometry) does not get the f32 walk
     // at all (view.f32_culling below), so its launches carry no stack
     ds->stack_bytes = static_cast<size_t>(flat.wide_depth <= 96 ? std::max<uint32_t>(flat.wide_depth, 1u) : 1u) * 128 * sizeof(uint32_t);
@@ -1664,7 +1670,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
             // any-order lanes postpone up to three siblings per level, each with its entry distance: at most 3 x depth + 1 entries of
             // 8 B per lane, capped at 32 (a lane that would need more hands its ray to the in-order walk, whose one-word entries
             // live in the same column: at least `depth` slots)
-            ds->any_cap = std::max<uint32_t>(flat.wide_depth, std::min<uint32_t>(3u * flat.wide_depth + 1u, 32u));
+            const uint32_t any_depth = ds->free_wide ? flat.free_depth : flat.wide_depth;
+            ds->any_cap = std::max<uint32_t>(flat.wide_depth, std::min<uint32_t>(3u * any_depth + 1u, 32u));
             if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = std::max<uint32_t>(flat.wide_depth, static_cast<uint32_t>(std::max(1, std::min(48, std::atoi(v)))));  // tests
             ds->stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
             if (ds->any_order == 2) {
@@ -1681,8 +1688,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 3;
         if (const char* v = std::getenv("RTP_BUILD_TIMING")) if (std::atoi(v) != 0)
-            std::fprintf(stderr, "[rtp build] 4-wide tree depth %u, %s walk (%u big primitives), %zu B of stack per block, %d traversal blocks per SM\n", flat.wide_depth,
-                         ds->any_order ? "any-order" : "in-order", flat.n_big, ds->stack_bytes, per_sm);
+            std::fprintf(stderr, "[rtp build] 4-wide tree depth %u (order-free tree: %u), %s walk (%u big primitives), %zu B of stack per block, %d traversal blocks per SM\n",
+                         flat.wide_depth, flat.free_depth, ds->any_order ? "any-order" : "in-order", flat.n_big, ds->stack_bytes, per_sm);
         ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (const char* v = std::getenv("RTP_TAIL_THRESHOLD")) ds->tail_threshold = static_cast<uint32_t>(std::max(0l, std::atol(v)));
         if (const char* v = std::getenv("RTP_TAIL_OFFER")) ds->tail_offer = std::atoi(v) != 0;
@@ -1707,6 +1714,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
 
     DSceneView& v = ds->view;
     v.nodes = ds->nodes; v.wide = ds->wide; v.wide_boxes = ds->wide_boxes; v.prims = ds->prims;
+    v.any_wide = ds->free_wide ? ds->free_wide : ds->wide; v.any_boxes = ds->free_wide ? ds->free_boxes : ds->wide_boxes;
     v.f32_culling = (flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96) ? 1u : 0u; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
     v.n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
     v.n_prims = static_cast<uint32_t>(flat.prims.size());

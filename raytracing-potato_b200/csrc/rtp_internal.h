@@ -96,6 +96,8 @@ struct DSceneView {  // passed by value to kernels
     const DNode* nodes;
     const DWide* wide;
     const double* wide_boxes;  // [node][child][min xyz, max xyz] exact f64 child boxes (counting kernels: violation check)
+    const DWide* any_wide;     // the tree the any-order lanes walk: `wide`, or the order-free tree of a big scene
+    const double* any_boxes;
     const DPrim* prims;
     const DAttr* attrs;
     const DMaterial* materials;
@@ -138,6 +140,9 @@ struct FlatScene {
     uint32_t n_reference_nodes = 0;  // 2n-1
     uint32_t device_depth = 0;       // of the culling tree the kernels walk
     bool any_ok = false;             // the any-order walk may be used on this scene (prepare_any_order, rtp_host.cpp)
+    std::vector<DWide> free_wide;    // second culling tree over the Morton order of the leaves (any-order walk of big scenes); may be empty
+    std::vector<double> free_boxes;
+    uint32_t free_depth = 0;
     uint32_t n_big = 0;
     uint32_t big[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double any_E = 0.0, any_A = 0.0;

@@ -739,10 +739,12 @@ def _mixed_rays(sc, n_inc=60000, seed=9):
                            edge_rays().view(A.RAY_DTYPE).reshape(-1)])
 
 
+@pytest.mark.parametrize("free_tree", ["0", "1"])
 @pytest.mark.parametrize("name", ["bunny_lambert", "bunny_triangles_only", "glass_bunny", "demo", "one_triangle", "field"])
-def test_any_order_walk_returns_the_reference_hits(gpu, monkeypatch, name):
+def test_any_order_walk_returns_the_reference_hits(gpu, monkeypatch, name, free_tree):
     """RTP_TRAVERSAL=any forces the any-order walk on every eligible ray of the scene; hits must be the oracle's bit for bit,
     no conservative-culling violation may be counted, and the walk must actually be cheaper than the in-order one"""
+    monkeypatch.setenv("RTP_FREE_TREE", free_tree)  # 1: the any-order lanes walk a second tree over the Morton order of the leaves
     sc = scenes.bunny_field(4, 2) if name == "field" else getattr(scenes, name)()
     rays = _mixed_rays(sc)
     if name == "field":
@@ -772,7 +774,8 @@ def test_any_order_walk_returns_the_reference_hits(gpu, monkeypatch, name):
     g0.close(); g1.close(); o.close()
 
 
-def test_any_order_walk_axis_aligned_geometry_and_exact_ties(gpu, monkeypatch):
+@pytest.mark.parametrize("free_tree", ["0", "1"])
+def test_any_order_walk_axis_aligned_geometry_and_exact_ties(gpu, monkeypatch, free_tree):
     """axis-aligned triangles have boxes of zero thickness, so their computed t falls below their own box entry about half the
     time (abnormal leaves): those rays must be walked again in the reference's order and still return the oracle's bits.
     Every triangle appears twice (exact ties: the later one in depth-first order wins), one ground sphere is the big primitive."""
@@ -814,6 +817,7 @@ def test_any_order_walk_axis_aligned_geometry_and_exact_ties(gpu, monkeypatch):
     import torch
 
     monkeypatch.setenv("RTP_TRAVERSAL", "any")
+    monkeypatch.setenv("RTP_FREE_TREE", free_tree)
     g = api.Scene(sc)
     assert_hits_equal_bits(g.hit(rays), want)
     d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()

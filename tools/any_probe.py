@@ -42,8 +42,9 @@ def main():
             rays2 = rays.clone()
             rays2[:, 3:6] = rays[perm, 3:6]
         ref = {}
-        for mode in ("inorder", "any"):
-            os.environ["RTP_TRAVERSAL"] = mode
+        for mode in ("inorder", "any", "any+free"):
+            os.environ["RTP_TRAVERSAL"] = mode.split("+")[0]
+            os.environ["RTP_FREE_TREE"] = "1" if mode.endswith("free") else "0"
             scene = api.Scene(sc)
             for tag, r in (("primary", rays), ("incoherent", rays2)):
                 hits = torch.empty((r.shape[0], 2), dtype=torch.float64, device="cuda")
@@ -55,7 +56,7 @@ def main():
                     same = f" same bits as in-order: {bool((ref[tag].view(torch.int64) == hits.view(torch.int64)).all())}"
                 else:
                     ref[tag] = hits.clone()
-                print(f"{name:12s} {mode:8s} {tag:10s} {mr:8.1f} Mrays/s  nodes {c.node_visits / m:6.2f} gates {c.leaf_gates / m:5.2f} tri {c.triangle_tests / m:5.2f} "
+                print(f"{name:12s} {mode:9s} {tag:10s} {mr:8.1f} Mrays/s  nodes {c.node_visits / m:6.2f} gates {c.leaf_gates / m:5.2f} tri {c.triangle_tests / m:5.2f} "
                       f"sph {c.sphere_tests / m:5.2f} viol {c.conservative_violations} rewalks {c.order_rewalks}{same}", flush=True)
             if name != "bunny":
                 W2, H2, spp = 1920, 1080, 2
@@ -64,7 +65,7 @@ def main():
                 p = api.render_params(W2, H2, spp, 8, seed=1, flags=A.RENDER_RAW_SUMS)
                 s = scene.render_device(p, cam2, acc.data_ptr(), acc.data_ptr() + W2 * H2 * 24, st, stats=True)
                 s = scene.render_device(p, cam2, acc.data_ptr(), acc.data_ptr() + W2 * H2 * 24, st, stats=True)
-                print(f"{name:12s} {mode:8s} render {W2}x{H2}x{spp}: {s.device_ms:.1f} ms, {s.rays / s.device_ms / 1e3:.1f} Mrays/s, sum {float(acc.sum()):.10e}", flush=True)
+                print(f"{name:12s} {mode:9s} render {W2}x{H2}x{spp}: {s.device_ms:.1f} ms, {s.rays / s.device_ms / 1e3:.1f} Mrays/s, sum {float(acc.sum()):.10e}", flush=True)
             scene.close()
         del os.environ["RTP_TRAVERSAL"]
 
