@@ -686,6 +686,7 @@ __device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc,
         return;
     }
 #define RTP_SEL(k) __funnelshift_rc(__funnelshift_rc(ch.x, ch.y, ((k) & 1u) << 5), __funnelshift_rc(ch.z, ch.w, ((k) & 1u) << 5), ((k) & 2u) << 4)
+    // (an L2 prefetch of the postponed child's record was measured 3 % slower on the bunny and on the C5 scene alike)
 #define RTP_PUSH(s)                                                                       \
     if ((s) != 0xFFFFFFFFu) {                                                             \
         stack[w.sp * stride] = make_uint2(RTP_SEL(s), (s) & ~3u);                         \
@@ -1527,7 +1528,6 @@ __global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ 
 
 constexpr int kPipeDepth = 3;
 constexpr size_t kAnyOrderBigScene = 262144;  // leaves from which the 4-blocks-per-SM variant is used
-constexpr size_t kAnyOrderAutoLeaves = 0;  // every eligible scene takes the any-order walk by default (measured faster from the 4,969-leaf bunny up)
 constexpr unsigned kQueueSlots = 64;
 static size_t chunk_rays() {  // rays per pipeline stage: 2^18 (16 MiB of rays) unless RTP_CHUNK_LOG2 says otherwise (tuning runs)
     static const size_t v = [] { const char* e = std::getenv("RTP_CHUNK_LOG2"); const int l = e ? std::atoi(e) : 18; return size_t(1) << std::max(10, std::min(24, l)); }();
@@ -1637,7 +1637,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         // RTP_TRAVERSAL=any | inorder overrides the choice
         const char* tv = std::getenv("RTP_TRAVERSAL");
         const bool f32_ok = flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96;
-        bool want = flat.prims.size() >= kAnyOrderAutoLeaves;
+        bool want = true;  // every eligible scene takes the any-order walk by default (measured faster from the 4,969-leaf bunny up)
         if (tv && std::string(tv) == "any") want = true;
         if (tv && std::string(tv) == "inorder") want = false;
         if (const char* v = std::getenv("RTP_F32_CULLING")) if (std::atoi(v) == 0) want = false;
@@ -1942,7 +1942,10 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
                 int rc;
                 // a launch of at most tail_threshold paths (a 32x32 tile of main.rs:32, say) runs as generate + ONE tail-mode launch.
                 // RTP_TAIL_OFFER=1 also offers every later queue of a big launch to the tail kernel, which declines the ones above
-                // the threshold; measured on C1 it is no faster than trace/shade pairs (both are bound by per-ray latency), so off.
+                // the threshold; measured on C1 it is no faster than trace/shade pairs, and neither is handing the sparse late bounces
+                // to one tail launch chosen from the previous launch's queue sizes (19 -> 12 launches per C1 frame, same 2.05 ms):
+                // a late bounce costs the latency of ONE ray segment (~30 us of dependent instructions, tools/small_batches.py),
+                // not a launch.
                 const bool tail_certain = total <= ds->tail_threshold;
                 if (ds->tail_threshold && (tail_certain || (ds->tail_offer && b > 0))) {
                     TailArgs ta{ds->wave, rp, ds->scratch, b, ds->tail_threshold};
