@@ -1723,7 +1723,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     v.any_order = ds->any_order ? 1u : 0u;
     v.any_cap = ds->any_cap;
     v.n_big = flat.n_big;
-    std::memcpy(v.big, flat.big, sizeof v.big);
+    v._pad_any = 0;
     v.any_E = flat.any_E; v.any_A = flat.any_A;
     v.any_Ef = std::nextafter(static_cast<float>(flat.any_E), std::numeric_limits<float>::infinity());  // >= any_E
     v.any_Af = std::nextafter(static_cast<float>(flat.any_A), std::numeric_limits<float>::infinity());

@@ -114,7 +114,7 @@ struct DSceneView {  // passed by value to kernels
     uint32_t any_order;    // 1: eligible rays of this scene use it
     uint32_t any_cap;      // entries of the per-lane any-order stack
     uint32_t n_big;        // primitives exempt from distance culling (all spheres, outsized triangles), at most kMaxBig
-    uint32_t big[7];       // slot | kind << 31 (first seven; informational)
+    uint32_t _pad_any;
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
     float any_Ef, any_Af;  // the same, rounded up to f32
