@@ -339,7 +339,7 @@ def main():
                      "frac": f64_ops / (kernel_ms * 1e-3) / fp64_peak, "peak_source": "148 SM x 64 FP64 lanes x median SM clock during the run"},
             "l2": {"bytes_per_launch": scene_bytes, "achieved_gbs": scene_bytes / (kernel_ms * 1e-3) / 1e9},
             "l1_note": "scene bytes are served by L1/L2, not HBM",
-            "issue": {"note": "binding resource per ncu (profiles/r01_trace_any_c2.md): smsp__issue_active 61 % of peak at 22.7 of 32 lanes per instruction, 29 % warp occupancy (96 registers, 5 blocks of 128 per SM), L1 hit rate 69 %; HBM 7 % of peak"},
+            "issue": {"note": "binding resource per ncu (profiles/r01_trace_any_c2.md): smsp__issue_active 61 % of peak at 22.9 of 32 lanes per instruction, 70 warp-instructions per ray, 29 % warp occupancy (96 registers, 5 blocks of 128 per SM), L1 hit rate 68 %; HBM 7 % of peak"},
             "per_ray": {"node_visits": cst.node_visits / N_RAYS, "leaf_gates": cst.leaf_gates / N_RAYS, "triangle_tests": cst.triangle_tests / N_RAYS, "sphere_tests": cst.sphere_tests / N_RAYS,
                         "conservative_violations": int(cst.conservative_violations)},
         },

@@ -1572,6 +1572,7 @@ struct DeviceScene {
     int tail_blocks = 0;               // grid of the tail-mode traversal kernel
     uint32_t tail_threshold = 65536;   // RTP_TAIL_THRESHOLD: a launch this small is finished by one tail-mode launch (0 = never)
     bool tail_offer = false;           // RTP_TAIL_OFFER
+    size_t queue_budget_bytes = size_t(4) << 30;  // memory the integrator's per-launch buffers may take (set at upload from the free HBM)
     bool use_simple_render = false;    // RTP_RENDER_KERNEL=simple
     bool debug_sync = false;           // RTP_DEBUG_SYNC
     double* frame = nullptr; size_t frame_elems = 0;
@@ -1685,6 +1686,9 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 0>, 128, ds->stack_bytes);
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 0>, 128, ds->stack_bytes);
         }
+        size_t free_b = 0, total_b = 0;
+        if (e == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            ds->queue_budget_bytes = std::max<size_t>(size_t(1) << 30, std::min<size_t>(size_t(24) << 30, free_b / 6));
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * 3;
         if (const char* v = std::getenv("RTP_BUILD_TIMING")) if (std::atoi(v) != 0)
@@ -1893,10 +1897,13 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
 
     const size_t npix = static_cast<size_t>(tw) * th;
     const uint32_t ns_total = p->sample_end - p->sample_begin;
-    // samples per launch: about 8 Mi paths (scratch 256 MiB; wavefront queues 176 B + 48 B x max_bounce per path, so the
-    // path budget shrinks for deep stacks to keep the queues under ~4 GiB)
+    // samples per launch: up to 32 Mi paths (wavefront queues 176 B + 48 B x max_bounce per path, scratch 32 B), within the memory
+    // budget fixed when the scene was uploaded (a sixth of the free HBM, at most 24 GiB). Big launches matter: every launch pays
+    // the fill and drain of ~2 x max_bounce kernels and the latency-bound sparse late bounces once (1080p x 64 spp of the C4
+    // scene: 111 ms in 16 launches of 8 Mi paths, 92 ms in 4 launches of 32 Mi)
     const bool wave = !ds->use_simple_render;
-    size_t path_budget = wave ? std::min<size_t>(size_t(8) << 20, (size_t(4) << 30) / (176 + 48 * static_cast<size_t>(p->max_bounce))) : (size_t(8) << 20);
+    const size_t per_path = wave ? 176 + 48 * static_cast<size_t>(p->max_bounce) + 32 : 32;
+    size_t path_budget = std::max<size_t>(size_t(1) << 20, std::min<size_t>(size_t(32) << 20, ds->queue_budget_bytes / per_path));
     if (const char* v = std::getenv("RTP_PATH_BUDGET")) path_budget = std::max<size_t>(1, static_cast<size_t>(std::atoll(v)));  // tests: force several launches per frame
     uint32_t per_launch = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(ns_total ? ns_total : 1, path_budget / npix)));
     const size_t need = npix * per_launch;

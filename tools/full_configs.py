@@ -32,8 +32,8 @@ acc = torch.zeros((w * h * 4,), dtype=torch.float64, device=dev)
 sb, se = rdist.sample_range(spp, rank, world)
 p = api.render_params(w, h, spp, 8, seed=1, sample_begin=sb, sample_end=se, flags=A.RENDER_RAW_SUMS)
 stream = torch.cuda.current_stream().cuda_stream
-# warm-up: 1 spp + the collective
-pw = api.render_params(w, h, spp, 8, seed=1, sample_begin=sb, sample_end=sb + 1, flags=A.RENDER_RAW_SUMS)
+# warm-up: up to 8 spp (enough paths for a full-size launch, so the per-launch buffers are allocated before the timed region) + the collective
+pw = api.render_params(w, h, spp, 8, seed=1, sample_begin=sb, sample_end=sb + min(se - sb, 8), flags=A.RENDER_RAW_SUMS)
 scene.render_device(pw, cam, acc.data_ptr(), acc.data_ptr() + w * h * 24, stream)
 rdist.reduce_frame(acc)
 if world > 1:
