@@ -882,3 +882,57 @@ def test_any_order_stack_overflow_hands_the_ray_to_the_in_order_walk(gpu, monkey
         assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
         g.close()
     o.close()
+
+
+@pytest.mark.parametrize("name", ["bunny_lambert", "demo"])
+def test_any_order_walk_unusual_rays(gpu, monkeypatch, name):
+    """rays at the edge of the any-order walk's preconditions: zero and negative t_min (not eligible), finite t_max before,
+    inside and behind the geometry, directions with one tiny component (huge 1/d: large slack, or outside the f32 walk), unnormalised
+    directions, distant origins (large |o|: large slack), origins on the geometry. Both visiting orders must return the oracle's bits."""
+    import torch
+
+    sc = getattr(scenes, name)()
+    rng = np.random.default_rng(77)
+    n = 80000
+    base = scenes.incoherent_rays(n, seed=21)
+    rays = base.copy()
+    k = n // 10
+    rays["t_min"][0 * k:1 * k] = 0.0
+    rays["t_min"][1 * k:2 * k] = -rng.uniform(0.0, 5.0, k)
+    rays["t_max"][2 * k:3 * k] = rng.uniform(0.0, 6.0, k)
+    tiny = rng.choice([1e-5, 1e-9, 1e-13, 1e-15, 3e-16, 1e-17, 1e-30], k)
+    axis = rng.integers(0, 3, k)
+    d = rays["direction"][3 * k:4 * k].copy()
+    d[np.arange(k), axis] = tiny * rng.choice([-1.0, 1.0], k)
+    rays["direction"][3 * k:4 * k] = d
+    rays["direction"][4 * k:5 * k] *= rng.choice([1e-6, 1e-3, 1e3, 1e6], k)[:, None]
+    far = rng.choice([1e2, 1e4, 1e7, 1e10], k)[:, None]
+    o = rays["origin"][5 * k:6 * k] * far
+    rays["origin"][5 * k:6 * k] = o
+    tgt = rng.uniform([-0.9, 0.0, -0.6], [0.6, 1.5, 0.58], (k, 3))
+    rays["direction"][5 * k:6 * k] = tgt - o
+    # origins on the geometry: the hit points of other rays, new directions, the reference's own scatter epsilon
+    orc = oracle.Scene(sc)
+    first = orc.hit(base[6 * k:8 * k])
+    ok = first["leaf"] != MISS
+    p = base["origin"][6 * k:8 * k] + first["t"][:, None] * base["direction"][6 * k:8 * k]
+    p[~ok] = base["origin"][6 * k:8 * k][~ok]
+    rays["origin"][6 * k:8 * k] = p
+    nd = rng.normal(size=(2 * k, 3))
+    rays["direction"][6 * k:8 * k] = nd / np.linalg.norm(nd, axis=1, keepdims=True)
+    rays["t_min"][6 * k:8 * k] = 1e-3
+    rays["t_min"][8 * k:9 * k] = rng.uniform(0.0, 4.0, k)  # t_min inside the scene
+    rays["t_max"][8 * k:9 * k] = rays["t_min"][8 * k:9 * k] + rng.uniform(0.0, 2.0, k)
+    want = orc.hit(rays)
+    d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((len(rays), 2), dtype=torch.float64, device="cuda")
+    for order in ("any", "inorder"):
+        monkeypatch.setenv("RTP_TRAVERSAL", order)
+        g = api.Scene(sc)
+        st = g.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+        assert_hits_equal_bits(d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1), want)
+        assert_hits_equal_bits(g.hit(rays), want)
+        assert st.conservative_violations == 0
+        g.close()
+    assert (want["leaf"] != MISS).mean() > 0.3
+    orc.close()
