@@ -1,5 +1,6 @@
-"""Short single-workload runner for ncu captures: python tools/prof_run.py c2|c3|c1|c4 [reps]
-c2 = 1920x1080 primary batch, c3 = 2^22 incoherent rays, c1 = 640x360x16spp bunny render, c4 = demo scene 960x540x8spp."""
+"""Short single-workload runner for ncu captures: python tools/prof_run.py c2|c3|c1|c4|c5s [reps]
+c2 = 1920x1080 primary batch, c3 = 2^22 incoherent rays, c1 = 640x360x16spp bunny render, c4 = demo scene 960x540x8spp,
+c5s = 3840x2160 primary batch against a 32x16 bunny field (2,543,617 leaves, scene in HBM)."""
 import os
 import sys
 
@@ -18,14 +19,15 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     api.init(0)
     st = torch.cuda.current_stream().cuda_stream
-    sc = scenes.demo() if what == "c4" else scenes.bunny_lambert()
+    sc = scenes.demo() if what == "c4" else (scenes.bunny_field(32, 16) if what == "c5s" else scenes.bunny_lambert())
     scene = api.Scene(sc)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if what in ("c2", "c3"):
-        if what == "c2":
-            cam = api.Camera(1920 / 1080, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
-            rays = torch.empty((1920 * 1080, 8), dtype=torch.float64, device="cuda")
-            api.camera_rays_device(cam, 1920, 1080, rays.data_ptr(), st)
+    if what in ("c2", "c3", "c5s"):
+        if what in ("c2", "c5s"):
+            W, H = (1920, 1080) if what == "c2" else (3840, 2160)
+            cam = api.Camera(W / H, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+            rays = torch.empty((W * H, 8), dtype=torch.float64, device="cuda")
+            api.camera_rays_device(cam, W, H, rays.data_ptr(), st)
         else:
             rays = torch.from_numpy(scenes.incoherent_rays(1 << 22).view(np.float64).reshape(-1, 8)).cuda()
         hits = torch.empty((rays.shape[0], 2), dtype=torch.float64, device="cuda")
