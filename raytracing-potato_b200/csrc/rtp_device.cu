@@ -1559,7 +1559,7 @@ struct DeviceScene {
     int any_order = 0;                 // 1, 2: eligible rays take the any-order walk (RTP_TRAVERSAL), kernel variant ANY = 1 or 2
     uint32_t any_cap = 0;              // any-order stack entries per lane
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
-    Tuning tune{16, 8, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
+    Tuning tune{16, 6, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
