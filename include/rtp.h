@@ -225,6 +225,11 @@ typedef struct rtp_scene_info {
     uint32_t depth;          /* max number of nodes on a root→leaf path */
     uint32_t root_kind;
     uint64_t device_bytes;   /* HBM held by the scene */
+    uint32_t culling_depth;  /* levels of the 4-wide culling tree the kernels walk (0 for a List root)            */
+    uint32_t any_order;      /* front-to-back walk: 0 = not used; rtp_scene_get_info: 1 / 2 = kernel build in use;
+                                rtp_bvh_build_order: 1 = the scene is eligible                                     */
+    uint32_t n_big;          /* primitives exempt from distance culling (spheres, outsized triangles)             */
+    uint32_t free_tree_depth;/* levels of the order-free culling tree of the any-order lanes, 0 if there is none  */
 } rtp_scene_info;
 
 typedef struct rtp_scene rtp_scene; /* opaque, immutable after creation */

@@ -151,6 +151,10 @@ class SceneInfo(C.Structure):
         ("depth", C.c_uint32),
         ("root_kind", C.c_uint32),
         ("device_bytes", C.c_uint64),
+        ("culling_depth", C.c_uint32),
+        ("any_order", C.c_uint32),
+        ("n_big", C.c_uint32),
+        ("free_tree_depth", C.c_uint32),
     ]
 
 

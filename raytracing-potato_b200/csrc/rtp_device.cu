@@ -2067,6 +2067,8 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
         std::vector<DNode>().swap(s->flat.nodes);
         std::vector<DWide>().swap(s->flat.wide);
         std::vector<double>().swap(s->flat.wide_boxes);
+        std::vector<DWide>().swap(s->flat.free_wide);
+        std::vector<double>().swap(s->flat.free_boxes);
         std::vector<DPrim>().swap(s->flat.prims);
         std::vector<DAttr>().swap(s->flat.attrs);
         std::vector<std::vector<uint8_t>>().swap(s->flat.images);
@@ -2088,6 +2090,9 @@ int rtp_scene_get_info(const rtp_scene* scene, rtp_scene_info* info) {
     info->n_leaves = scene->n_leaves; info->n_nodes = scene->n_nodes;
     info->depth = scene->flat.depth; info->root_kind = scene->flat.root_kind;
     info->device_bytes = device_scene_bytes(scene->dev);
+    info->culling_depth = scene->flat.root_kind == RTP_ROOT_BVH ? scene->flat.wide_depth : 0u;
+    info->any_order = scene->dev ? static_cast<uint32_t>(scene->dev->any_order) : 0u;
+    info->n_big = scene->flat.n_big; info->free_tree_depth = scene->flat.free_depth;
     return RTP_OK;
 }
 
@@ -2104,6 +2109,8 @@ int rtp_bvh_build_order(const rtp_scene_desc* desc, uint32_t* leaf_ids_out, size
             info->n_leaves = static_cast<uint32_t>(flat.prims.size());
             info->n_nodes = flat.root_kind == RTP_ROOT_BVH ? flat.n_reference_nodes : 0u;
             info->depth = flat.depth; info->root_kind = flat.root_kind; info->device_bytes = 0;
+            info->culling_depth = flat.root_kind == RTP_ROOT_BVH ? flat.wide_depth : 0u;
+            info->any_order = flat.any_ok ? 1u : 0u; info->n_big = flat.n_big; info->free_tree_depth = flat.free_depth;
         }
         return RTP_OK;
     } catch (const std::exception& e) {

@@ -194,3 +194,46 @@ def test_product_does_not_reference_the_oracle():
                 assert "rtp_oracle" not in text and "liboracle" not in text and "import oracle" not in text, os.path.join(dirpath, f)
     out = subprocess.run(["ldd", A.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_traversal_plan_of_scenes():
+    """host half of the any-order walk (prepare_any_order, rtp_host.cpp), no device needed: which primitives are
+    exempt from distance culling, which scenes are eligible at all, and that small scenes get the order-free tree"""
+    _, info = api.bvh_build_order(scenes.bunny_lambert())
+    assert (info.any_order, info.n_big) == (1, 1)  # the ground sphere
+    assert 0 < info.culling_depth <= 16 and 0 < info.free_tree_depth <= 16
+    _, info = api.bvh_build_order(scenes.demo())
+    assert (info.any_order, info.n_big) == (1, 3)  # earth, light and ground spheres
+    _, info = api.bvh_build_order(scenes.two_balls())
+    assert (info.any_order, info.n_big) == (1, 2)
+    _, info = api.bvh_build_order(scenes.three_balls())  # a List root has no culling tree
+    assert (info.any_order, info.culling_depth, info.free_tree_depth) == (0, 0, 0)
+
+    mats = [api.Material.new(api.Scatter.Lambert, api.Absorb.WhiteBody, api.Emit.NONE)]
+
+    def scene_of(hittables, meshes=()):
+        return api.ExampleScene(scenes._bunny_camera(), api.SceneData(mats, [], list(meshes)), "bvh", hittables, api.Emit.SkyGradient)
+
+    nine = api.Hittable.concat([api.Hittable.Sphere([x, 0.0, 0.0], 0.4, 0) for x in range(9)])
+    _, info = api.bvh_build_order(scene_of(nine))  # more exempt primitives than the walk allows: the scene keeps the in-order walk
+    assert info.any_order == 0
+    eight = api.Hittable.concat([api.Hittable.Sphere([x, 0.0, 0.0], 0.4, 0) for x in range(8)])
+    _, info = api.bvh_build_order(scene_of(eight))
+    assert (info.any_order, info.n_big) == (1, 8)
+    inverted = api.Hittable.concat([api.Hittable.Sphere([0.0, 0.0, 0.0], -0.5, 0), api.Hittable.Sphere([2.0, 0.0, 0.0], 0.5, 0)])
+    _, info = api.bvh_build_order(scene_of(inverted))  # an inverted leaf box: reference topology, literal slab test, in-order walk
+    assert info.any_order == 0
+
+    # a fine grid of small triangles on a ground made of two huge ones: only the two huge triangles are exempt
+    pos, idx = [], []
+    for x in range(12):
+        for y in range(12):
+            b = len(pos)
+            pos += [[0.1 * x, 0.1 * y, 0.0], [0.1 * x + 0.1, 0.1 * y, 0.0], [0.1 * x, 0.1 * y + 0.1, 0.05]]
+            idx += [b, b + 1, b + 2]
+    b = len(pos)
+    pos += [[-500.0, -500.0, -1.0], [500.0, -500.0, -1.0], [500.0, 500.0, -1.0], [-500.0, 500.0, -1.0]]
+    idx += [b, b + 1, b + 2, b, b + 2, b + 3]
+    mesh = api.Mesh.from_arrays(pos, indices=idx, material=0)
+    _, info = api.bvh_build_order(scene_of(api.Hittable.triangles_of(mesh, 0), [mesh]))
+    assert (info.any_order, info.n_big, info.n_leaves) == (1, 2, 146)
