@@ -119,7 +119,9 @@ def hit_sphere(center, radius, o, d, t_min, t_max):  # hittable.rs:39-63 (uv not
         if t < t_min or t > t_max:
             return None
     position = add(o, scale(t, d))
-    return t, position, normalize(sub(position, center))
+    normal = normalize(sub(position, center))
+    uv = (0.5 - math.atan2(normal[2], normal[0]) / math.tau, math.asin(normal[1]) / math.pi + 0.5)  # hittable.rs:61
+    return t, position, normal, uv
 
 
 class Restated:
@@ -145,12 +147,25 @@ class Restated:
                 best = (r, int(h["material"]))
         return best
 
-    def texture(self, tid):
+    def texture(self, tid, uv):  # texture.rs:20-49
         t = self.sc.scene_data.texture_table[tid]
-        assert t.kind == A.TEXTURE_SOLID
-        return tuple(float(x) for x in t.color)
+        if t.kind == A.TEXTURE_SOLID:
+            return tuple(float(x) for x in t.color)
+        assert t.kind == A.TEXTURE_IMAGE
+        h, w = t.image.shape[:2]
 
-    def emit(self, e, d, normal):  # material.rs:49-60
+        def texel(x, n):  # (x * n).clamp(0, n - 1) as u32: truncation, NaN -> 0
+            v = x * float(n)
+            if v != v:
+                return 0
+            return int(min(max(v, 0.0), float(n) - 1.0))
+
+        px = t.image[texel(uv[1], h), texel(uv[0], w)]  # Array2d::get(i, j) = data[i + j * width], row 0 at the bottom
+        return (float(px[0]) / 255.0, float(px[1]) / 255.0, float(px[2]) / 255.0)
+
+    def emit(self, e, d, normal, uv):  # material.rs:49-60
+        if e.kind == A.EMIT_SKY_SPHERE:
+            return self.texture(e.texture, uv)
         if e.kind == A.EMIT_NONE:
             return (0.0, 0.0, 0.0)
         if e.kind == A.EMIT_COLOR:
@@ -161,14 +176,14 @@ class Restated:
         t = 0.5 * (d[1] / math.sqrt(dot(d, d)) + 1.0)
         return add(scale(1.0 - t, (1.0, 1.0, 1.0)), scale(t, (0.5, 0.7, 1.0)))
 
-    def absorb(self, a):  # material.rs:74-81
+    def absorb(self, a, uv):  # material.rs:74-81
         if a.kind == A.ABSORB_BLACKBODY:
             return (0.0, 0.0, 0.0)
         if a.kind == A.ABSORB_WHITEBODY:
             return (1.0, 1.0, 1.0)
         if a.kind == A.ABSORB_ALBEDO:
             return tuple(float(x) for x in a.color)
-        return self.texture(a.texture)
+        return self.texture(a.texture, uv)
 
     def scatter(self, s, d, position, normal, rng):  # material.rs:27-34, 115-180; returns the scattered direction or None
         if s.kind == A.SCATTER_NONE:
@@ -198,12 +213,14 @@ class Restated:
         self.rays += 1
         hit = self.scene_hit(o, d, RAY_EPSILON, INF)
         if hit is None:
-            return self.emit(self.sc.background, d, d), False
-        (t, position, normal), mid = hit
+            # Hit::at_infinity (utility.rs:93-100): the direction stands in for position and normal, equirectangular uv
+            uv_inf = (0.5 - math.atan2(d[2], d[0]) / math.tau, math.asin(d[1]) / math.pi + 0.5) if self.sc.background.kind == A.EMIT_SKY_SPHERE else None
+            return self.emit(self.sc.background, d, d, uv_inf), False
+        (t, position, normal, uv), mid = hit
         mat = self.sc.scene_data.material_table[mid]
         out_dir = self.scatter(mat.scatter, d, position, normal, rng)  # order: scatter, absorb, emit (material.rs:104-110)
-        absorb = self.absorb(mat.absorb)
-        emit = self.emit(mat.emit, d, normal)
+        absorb = self.absorb(mat.absorb, uv)
+        emit = self.emit(mat.emit, d, normal, uv)
         if out_dir is None:
             return add(emit, (0.0, 0.0, 0.0)), True
         if depth - 1 == 0:
@@ -248,9 +265,22 @@ def zoo_scene():
     return api.ExampleScene(camera, api.SceneData(materials, textures, []), "list", root, api.Emit.SkyGradient)
 
 
-@pytest.mark.parametrize("name,depth", [("three_balls", 8), ("zoo", 8), ("zoo", 2), ("three_balls", 1)])
+def textured_scene():
+    """earthmap.tga on a Lambert sphere and on an emitter, the synthetic sky panorama as SkySphere background (unnormalised
+    directions reach asin through the thin lens' non-unit camera basis): sphere uv, Hit::at_infinity uv and sample_image"""
+    from rtp_b200 import assets
+
+    sc = zoo_scene()
+    sc.scene_data.texture_table += [api.Texture.Image(assets.earthmap()), api.Texture.Image(assets.sky_panorama())]
+    sc.scene_data.material_table[4] = api.Material.new(api.Scatter.Lambert, api.Absorb.AlbedoMap(1), api.Emit.NONE)
+    sc.scene_data.material_table[1] = api.Material.new(api.Scatter.Metal(0.1), api.Absorb.AlbedoMap(1), api.Emit.NONE)
+    sc.background = api.Emit.SkySphere(2)
+    return sc
+
+
+@pytest.mark.parametrize("name,depth", [("three_balls", 8), ("zoo", 8), ("zoo", 2), ("three_balls", 1), ("textured", 8)])
 def test_pure_python_integrator_equals_oracle_path_by_path(name, depth):
-    sc = scenes.three_balls() if name == "three_balls" else zoo_scene()
+    sc = scenes.three_balls() if name == "three_balls" else (zoo_scene() if name == "zoo" else textured_scene())
     w, h, spp, seed = 36, 24, 3, 5
     o = oracle.Scene(sc)
     r = Restated(sc, w, h, depth, seed)
@@ -274,4 +304,71 @@ def test_pure_python_integrator_equals_oracle_path_by_path(name, depth):
             hits += 1.0 if hit else 0.0
         want = tuple(x / float(spp) for x in acc)
         assert np.array(want).tobytes() == img[j, i].tobytes() and fg[j, i] == hits / float(spp)
+    o.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# procedural textures (texture.rs:51-119, randomness.rs:86-110) restated with Python integers
+# ---------------------------------------------------------------------------------------------
+
+def _wrap(x):  # Wrapping<isize>: two's complement, 64 bits
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >> 63 else x
+
+
+def noise_integer(x, y, z, seed):  # randomness.rs:91-104; `>>` on isize is arithmetic, Python's `>>` on a negative int is too
+    a, b, c, d = 0x369E6D3B899E43CF, 0x53F89E7FFDA3B07D, 0x3B13C1CA4937E629, 0x577C2C6E4019D645
+    h = _wrap(_wrap(_wrap(_wrap(a * x) + _wrap(b * y)) + _wrap(c * z)) + _wrap(d * seed))
+    h = _wrap((h >> 13) ^ h)
+    return _wrap(_wrap(h * _wrap(_wrap(_wrap(h * h) * 60493) + 19990303)) + 1376312589)
+
+
+def noise_real(x, y, z, seed):  # randomness.rs:107-109: isize as f64 (round to nearest) / isize::MAX as f64 (= 2^63)
+    return float(noise_integer(x, y, z, seed)) / float((1 << 63) - 1)
+
+
+def sample_noise(p, seed):  # texture.rs:62-68
+    x = noise_real(math.floor(p[0]), math.floor(p[1]), math.floor(p[2]), seed)
+    return 0.5 * x + 0.5
+
+
+def sample_perlin(p, seed):  # texture.rs:70-119
+    fl = [math.floor(v) for v in p]
+    cl = [v + 1 for v in fl]
+
+    def grad_dot(cx, cy, cz):
+        g = (noise_real(cx, cy, cz, seed + 1), noise_real(cx, cy, cz, seed + 2), noise_real(cx, cy, cz, seed + 3))
+        return dot((p[0] - float(cx), p[1] - float(cy), p[2] - float(cz)), g)
+
+    k1, k2 = grad_dot(fl[0], fl[1], fl[2]), grad_dot(cl[0], fl[1], fl[2])
+    k3, k4 = grad_dot(fl[0], cl[1], fl[2]), grad_dot(cl[0], cl[1], fl[2])
+    k5, k6 = grad_dot(fl[0], fl[1], cl[2]), grad_dot(cl[0], fl[1], cl[2])
+    k7, k8 = grad_dot(fl[0], cl[1], cl[2]), grad_dot(cl[0], cl[1], cl[2])
+    t = [p[k] - float(fl[k]) for k in range(3)]
+    t = [(v * (v * 6.0 - 15.0) + 10.0) * v * v * v for v in t]
+
+    def mix(a, b, w):
+        return (b - a) * w + a
+
+    k12, k34, k56, k78 = mix(k1, k2, t[0]), mix(k3, k4, t[0]), mix(k5, k6, t[0]), mix(k7, k8, t[0])
+    return 0.5 * mix(mix(k12, k34, t[1]), mix(k56, k78, t[1]), t[2]) + 0.5
+
+
+def test_procedural_textures_equal_python_restatement():
+    sc = scenes.two_balls()
+    sc.scene_data.texture_table += [api.Texture.Noise(3), api.Texture.Noise(-77), api.Texture.Perlin(12345), api.Texture.Perlin(-1)]
+    o = oracle.Scene(sc)
+    rng = np.random.default_rng(9)
+    pts = np.concatenate([rng.uniform(-40.0, 40.0, (300, 3)), rng.uniform(-1e6, 1e6, (50, 3)), np.round(rng.uniform(-5, 5, (30, 3))),
+                          np.array([[0.0, 0.0, 0.0], [-0.0, 0.5, -0.5], [1e-300, -1e-300, 0.999999999999], [2.5, -3.5, 4.5]])])
+    for p in pts:
+        p = [float(v) for v in p]
+        for tid, seed in ((4, 3), (5, -77)):
+            want = sample_noise(p, seed)
+            got = o.texture_sample(tid, p, [0.0, 0.0])
+            assert np.float64(want).tobytes() == got[0].tobytes() and got[0] == got[1] == got[2], (p, seed, want, got)
+        for tid, seed in ((3, 0), (6, 12345), (7, -1)):  # texture 3 is two_balls' own Perlin(0)
+            want = sample_perlin(p, seed)
+            got = o.texture_sample(tid, p, [0.0, 0.0])
+            assert np.float64(want).tobytes() == got[0].tobytes() and got[0] == got[1] == got[2], (p, seed, want, got)
     o.close()
