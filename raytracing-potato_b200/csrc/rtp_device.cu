@@ -426,7 +426,7 @@ struct Tuning {
     int prim_batch;  // run primitive tests when at least this many lanes are parked at a leaf
     int fast_slab;   // 1: eligible rays use collide_fast
     int f32_culling; // 1: eligible rays cull with the conservative f32 walk
-    int walk_reps;   // culling-tree steps per warp vote
+    int _reserved;   // (was: culling-tree steps per warp vote; two is compiled in, 3 and 4 measured slower)
     int min_lanes;   // smallest number of rays a warp holds when the batch is small
 };
 
@@ -1708,7 +1708,6 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
         if (const char* v = std::getenv("RTP_F32_CULLING")) ds->tune.f32_culling = std::atoi(v) != 0;
         if (const char* v = std::getenv("RTP_MIN_LANES")) ds->tune.min_lanes = std::max(1, std::min(32, std::atoi(v)));
-        if (const char* v = std::getenv("RTP_WALK_REPS")) ds->tune.walk_reps = std::max(1, std::min(16, std::atoi(v)));
         if (!flat.boxes_finite) ds->tune.fast_slab = 0;
     }
     for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
