@@ -364,6 +364,13 @@ int rtp_rng_draws(uint64_t seed, uint32_t index_lo, uint32_t index_hi, uint32_t 
 #define RTP_RNG_STREAM_PATH 0u /* (pixel j*W+i, sample s): jitter, lens, scatter draws         */
 #define RTP_RNG_STREAM_RAYS 1u /* synthetic ray batches (bench / tests)                        */
 
+/* ---------------------------------------------------------------- diagnostics ----------- */
+
+/* Measured f64 instruction throughput of the bound device, in 1e9 unfused f64 operations (DMUL or DADD, the
+ * only kind the path executes: the reference never contracts a*b+c) per second: the denominator of the
+ * FP64 figure in bench.py's roofline (SURVEY.md 8d asks for a measured peak). Runs for a few ms. */
+int rtp_probe_fp64(double* gops_out);
+
 #ifdef __cplusplus
 }
 #endif

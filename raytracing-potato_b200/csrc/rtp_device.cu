@@ -1453,6 +1453,20 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
     }
 }
 
+// FP64 throughput probe (rtp_probe_fp64): eight independent multiply-then-add chains per thread; with --fmad=false each step
+// is one DMUL and one DADD, the instruction mix of the path itself
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* __restrict__ sink, double a, double b, int iters) {
+    double x[8];
+    for (int k = 0; k < 8; ++k) x[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = x[k] * a + b;
+    }
+    double s = 0.0;
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 123.456) sink[blockIdx.x] = s;  // never true: keeps the chains alive
+}
+
 // main.rs:78-87: per pixel, add the samples of this launch in sample order to the running sums; on the
 // last launch optionally divide by num_samples. acc is (r,g,b,foreground) per tile pixel.
 __global__ void __launch_bounds__(256) resolve_kernel(const double4* __restrict__ scratch, double4* __restrict__ acc, size_t npix, uint32_t n_samples,
@@ -2037,6 +2051,36 @@ int rtp_init(int device) {
     RTP_CUDA(cudaSetDevice(device));
     RTP_CUDA(cudaFree(nullptr));
     g_device = device;
+    return RTP_OK;
+}
+
+int rtp_probe_fp64(double* gops_out) {
+    if (!gops_out) return set_error(RTP_ERR_INVALID, "null argument");
+    int rc = require_device();
+    if (rc != RTP_OK) return rc;
+    cudaDeviceProp prop;
+    RTP_CUDA(cudaGetDeviceProperties(&prop, g_device));
+    double* sink = nullptr;
+    RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&sink), sizeof(double) * 4096));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, iters = 16384;
+    double best = 0.0;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; ++rep) {  // first repetition warms up
+        cudaEventRecord(e0);
+        fp64_probe_kernel<<<blocks, 256>>>(sink, 0.999999, 1e-6, iters);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && rep > 0 && ms > 0.f) best = std::max(best, 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e9);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (e != cudaSuccess) return set_error(RTP_ERR_CUDA, std::string("fp64 probe: ") + cudaGetErrorString(e));
+    *gops_out = best;
     return RTP_OK;
 }
 
