@@ -21,7 +21,7 @@ from rtp_b200 import api, scenes
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scene", nargs="?", default="bunny", choices=["three_balls", "two_balls", "earth", "one_triangle", "glass_bunny", "bunny", "bunny_lambert", "demo"])
+    ap.add_argument("scene", nargs="?", default="bunny", choices=["three_balls", "more_balls", "more_balls_optimized", "two_balls", "earth", "one_triangle", "glass_bunny", "bunny", "bunny_lambert", "demo"])
     ap.add_argument("--tiles", action="store_true")
     ap.add_argument("--out", default="output.tga")
     ap.add_argument("--seed", type=int, default=1)

@@ -1,8 +1,9 @@
 """Scene definitions: the reference's example scenes (example_scenes.rs) and the BASELINE.json configs.
 
 Each function returns an `ExampleScene` built through the same constructors the reference uses.
-`more_balls` is not restated: its geometry is drawn from rand 0.8's ChaCha12 stream
-(example_scenes.rs:98), which this build replaces by design.
+`more_balls` draws its geometry from `StdRng::from_seed([249; 32])` (example_scenes.rs:98), i.e. rand 0.8's ChaCha12 stream;
+`StdRngStream` restates that stream (the published ChaCha algorithm and rand_core's block-buffer reading order; the crates
+themselves are not vendored with the reference, so the sequence is pinned by the ChaCha known answers only).
 """
 from __future__ import annotations
 
@@ -35,6 +36,93 @@ def three_balls() -> ExampleScene:
         Hittable.Sphere([1.0, 0.0, -1.0], 0.5, 3),
     ])
     return ExampleScene(camera, SceneData(materials, textures, []), "list", root, Emit.SkyGradient)
+
+
+class StdRngStream:
+    """`rand::rngs::StdRng` of rand 0.8 (= rand_chacha's ChaCha12Rng) as far as the reference uses it: `from_seed(seed)` and
+    `gen::<f64>()`. State: the ChaCha constants, the 32 seed bytes as eight little-endian key words, a 64-bit block counter
+    (words 12-13) starting at 0, a 64-bit stream id (words 14-15) of 0; 12 rounds; the output is the keystream in order.
+    rand_core's BlockRng reads a u64 as (next word) << 32 | (this word); `Standard` maps it to [0, 1) as (u64 >> 11) * 2^-53."""
+
+    def __init__(self, seed: bytes, rounds: int = 12):
+        assert len(seed) == 32
+        self.key = [int.from_bytes(seed[4 * k:4 * k + 4], "little") for k in range(8)]
+        self.rounds, self.counter, self.buf, self.pos = rounds, 0, [], 0
+
+    def block(self, counter: int):
+        m = 0xFFFFFFFF
+        init = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + self.key + [counter & m, (counter >> 32) & m, 0, 0]
+        x = list(init)
+
+        def rotl(v, n):
+            return ((v << n) & m) | (v >> (32 - n))
+
+        def quarter(a, b, c, d):
+            x[a] = (x[a] + x[b]) & m; x[d] = rotl(x[d] ^ x[a], 16)
+            x[c] = (x[c] + x[d]) & m; x[b] = rotl(x[b] ^ x[c], 12)
+            x[a] = (x[a] + x[b]) & m; x[d] = rotl(x[d] ^ x[a], 8)
+            x[c] = (x[c] + x[d]) & m; x[b] = rotl(x[b] ^ x[c], 7)
+
+        for _ in range(self.rounds // 2):
+            quarter(0, 4, 8, 12); quarter(1, 5, 9, 13); quarter(2, 6, 10, 14); quarter(3, 7, 11, 15)
+            quarter(0, 5, 10, 15); quarter(1, 6, 11, 12); quarter(2, 7, 8, 13); quarter(3, 4, 9, 14)
+        return [(x[k] + init[k]) & m for k in range(16)]
+
+    def next_u32(self) -> int:
+        if self.pos == len(self.buf):
+            self.buf, self.pos = self.block(self.counter), 0
+            self.counter += 1
+        v = self.buf[self.pos]
+        self.pos += 1
+        return v
+
+    def next_u64(self) -> int:
+        lo = self.next_u32()
+        return (self.next_u32() << 32) | lo
+
+    def gen(self) -> float:
+        return float(self.next_u64() >> 11) * 2.0 ** -53
+
+
+def more_balls(optimized: bool = False) -> ExampleScene:
+    """example_scenes.rs:63-138 (List root) and :141-150 (`more_balls_optimized`: the same list under Bvh::new): a checkered
+    ground, three big spheres and 3,782 small ones with random materials"""
+    camera = Camera(1.0, FRAC_PI_2, 7.5, 0.02, Transformation.lookat([6.0, 2.0, 4.0], [0.0, 0.0, 0.0], [0.0, 1.0, 0.0]))
+    textures = [Texture.Checker(1, 2), Texture.Solid(rgb(0.2, 0.3, 0.1)), Texture.Solid(rgb(0.9, 0.9, 0.9))]
+    materials = [
+        Material.new(Scatter.Lambert, Absorb.AlbedoMap(0), Emit.NONE),
+        Material.new(Scatter.Lambert, Absorb.Albedo(rgb(0.1, 0.2, 0.5)), Emit.NONE),
+        Material.new(Scatter.Metal(0.0), Absorb.Albedo(rgb(0.8, 0.6, 0.2)), Emit.NONE),
+        Material.new(Scatter.Dielectric(1.5), Absorb.WhiteBody, Emit.NONE),
+    ]
+    root = [Hittable.Sphere([0.0, -1000.0, -1.0], 1000.0, 0), Hittable.Sphere([-4.0, 1.8, 0.0], 1.8, 1),
+            Hittable.Sphere([4.0, 1.8, 0.0], 1.8, 2), Hittable.Sphere([0.0, 1.8, 0.0], 1.8, 3)]
+    rng = StdRngStream(bytes([249] * 32))
+
+    def closed_range(lo, hi):  # randomness.rs:12-16
+        return lo + rng.gen() * (hi - lo)
+
+    for x in range(-31, 31):
+        for z in range(-31, 31):
+            if z == 0:
+                continue
+            radius = closed_range(0.1, 0.3)
+            cx = float(x) + closed_range(-0.5 + radius, 0.5 - radius)
+            cz = float(z) + closed_range(-0.5 + radius, 0.5 - radius)
+            root.append(Hittable.Sphere([cx, radius, cz], radius, len(materials)))
+            albedo = rgb(rng.gen(), rng.gen(), rng.gen())
+            if rng.gen() < 0.7:
+                materials.append(Material.new(Scatter.Lambert, Absorb.Albedo(albedo), Emit.NONE))
+            elif rng.gen() < 0.7:
+                materials.append(Material.new(Scatter.Metal(rng.gen()), Absorb.Albedo(albedo), Emit.NONE))
+            else:
+                materials.append(Material.new(Scatter.Dielectric(1.5), Absorb.WhiteBody, Emit.NONE))
+    return ExampleScene(camera, SceneData(materials, textures, []), "bvh" if optimized else "list", Hittable.concat(root), Emit.SkyGradient)
+
+
+def more_balls_optimized() -> ExampleScene:
+    """example_scenes.rs:141-150"""
+    return more_balls(True)
 
 
 def two_balls() -> ExampleScene:

@@ -217,7 +217,8 @@ def test_exact_tmax_is_accepted(bunny_pair):
     assert_hits_equal(h3, o.hit(r2), "shrunk t_max")
 
 
-@pytest.mark.parametrize("name", ["bunny_triangles_only", "glass_bunny", "demo", "three_balls", "two_balls", "earth", "one_triangle"])
+@pytest.mark.parametrize("name", ["bunny_triangles_only", "glass_bunny", "demo", "three_balls", "two_balls", "earth", "one_triangle", "more_balls",
+                                  "more_balls_optimized"])
 def test_other_scenes_closest_hit(gpu, name):
     sc = getattr(scenes, name)()
     g, o = api.Scene(sc), oracle.Scene(sc)
@@ -242,6 +243,7 @@ IMG_FRAC = 1e-3
 @pytest.mark.parametrize("name,w,h,spp", [
     ("bunny_lambert", 320, 180, 4), ("bunny", 160, 90, 2), ("glass_bunny", 160, 90, 4), ("demo", 192, 108, 4),
     ("three_balls", 128, 128, 8), ("two_balls", 128, 128, 4), ("earth", 128, 128, 4), ("one_triangle", 128, 128, 2),
+    ("more_balls_optimized", 160, 160, 2), ("more_balls", 48, 48, 1),
 ])
 def test_render_matches_oracle(gpu, name, w, h, spp):
     sc = getattr(scenes, name)()

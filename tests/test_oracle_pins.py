@@ -511,3 +511,42 @@ def test_texture_sampling_rules():
     assert p0[0] == 0.5                                                              # perlin is 0 on lattice points
     p1, p2 = o.texture_sample(3, [2.3, 3.3, 4.3], [0, 0]), o.texture_sample(3, [2.3000001, 3.3, 4.3], [0, 0])
     assert 0 <= p1[0] <= 1 and abs(p1[0] - p2[0]) < 1e-5
+
+
+def test_stdrng_stream_and_more_balls_scene():
+    """`StdRng::from_seed([249; 32])` (example_scenes.rs:98) restated as ChaCha12 (scenes.StdRngStream): the block function is pinned by
+    the published zero-key known answers for 8, 12 and 20 rounds; the scene generator (example_scenes.rs:63-138) by its invariants"""
+    kat = {20: "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586",
+           12: "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be",
+           8: "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e984ce172b9216f419f445367456d5619314a42a3da86b001387bfdb80e0cfe42"}
+    for rounds, want in kat.items():
+        r = scenes.StdRngStream(bytes(32), rounds)
+        assert b"".join(w.to_bytes(4, "little") for w in r.block(0)).hex() == want
+    r = scenes.StdRngStream(bytes(32))
+    words = [r.next_u32() for _ in range(40)]  # the keystream in order, block after block (64-bit counter in words 12-13)
+    assert words[:16] == r.block(0) and words[16:32] == r.block(1) and words[32:] == r.block(2)[:8]
+    r = scenes.StdRngStream(bytes(32))
+    lo, hi = r.block(0)[0], r.block(0)[1]
+    assert r.next_u64() == (hi << 32) | lo  # rand_core BlockRng::next_u64: low word first
+    r = scenes.StdRngStream(bytes([249] * 32))
+    assert all(0.0 <= r.gen() < 1.0 for _ in range(1000))
+
+    sc = scenes.more_balls()
+    h = sc.hittables
+    assert len(h) == 4 + 62 * 61 and len(sc.scene_data.material_table) == len(h) and sc.root_kind == "list"
+    small = h[4:]
+    assert (small["radius"] >= 0.1).all() and (small["radius"] <= 0.3).all() and (small["center"][:, 1] == small["radius"]).all()
+    cell = np.array([(x, z) for x in range(-31, 31) for z in range(-31, 31) if z != 0], dtype=np.float64)
+    assert (np.abs(small["center"][:, [0, 2]] - cell) <= 0.5 - small["radius"][:, None] + 1e-12).all()  # each ball stays inside its cell
+    assert (small["material"] == np.arange(4, len(h))).all()
+    kinds = np.array([m.scatter.kind for m in sc.scene_data.material_table[4:]])
+    frac = [(kinds == k).mean() for k in (A.SCATTER_LAMBERT, A.SCATTER_METAL, A.SCATTER_DIELECTRIC)]
+    assert abs(frac[0] - 0.7) < 0.03 and abs(frac[1] - 0.21) < 0.03 and abs(frac[2] - 0.09) < 0.02, frac
+    # more_balls_optimized: the same list under Bvh::new; closest hits agree with the linear scan
+    ob, ol = oracle.Scene(scenes.more_balls_optimized()), oracle.Scene(sc)
+    assert ob.info().n_nodes == 2 * len(h) - 1
+    cam = api.Camera(1.0, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+    rays = oracle.camera_rays(cam, 96, 96)
+    hb, hl = ob.hit(rays), ol.hit(rays)
+    assert (hb["leaf"] == hl["leaf"]).all() and hb["t"].tobytes() == hl["t"].tobytes() and (hb["leaf"] != 0xFFFFFFFF).mean() > 0.5
+    ob.close(); ol.close()
