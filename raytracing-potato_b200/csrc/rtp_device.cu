@@ -575,8 +575,19 @@ __device__ __forceinline__ bool any_slack(const Walker& w, const DSceneView& sc,
     const float a0 = __fmul_ru(__fmul_ru(__fadd_ru(eta, __fmul_ru(u, P)), I), 1.0000002f);
     const float a1 = __fmul_ru(__fmul_ru(__fmul_ru(K, 6.0f), __fmul_ru(PE, E)), 1.3333334f);
     const float a2 = __fmul_ru(3.0f * u, __double2float_ru(fabs(w.tmin)));
-    s0f = __fmul_ru(4.0f, __fadd_ru(__fadd_ru(a0, a1), a2));
-    s1f = __fmul_ru(4.0f, __fmul_ru(__fadd_ru(__fmul_ru(__fmul_ru(K, 6.0f), DE2), 5.0f * u), 1.3333334f));
+    float a3 = 0.f;
+    if (sc.any_Rf >= 0.f) {
+        // spheres that are not big (hittable.rs:39-57): delta = half_b^2 - a (|o-c|^2 - r^2) carries an absolute error of at most
+        // 40 u |d|^2 S with S = |o-c|^2 + r^2, a root sqrt(40 u S) / |d|; a grazing ray adds the same once for the root gap and
+        // once for the closest point lying that far outside the sphere (times |1/d| on the slab axis): 3 sqrt(40 u S) |1/d|max
+        const float Po = __double2float_ru(fmax(fmax(fabs(w.o.x), fabs(w.o.y)), fabs(w.o.z)));
+        const float oc = __fadd_ru(Po, sc.any_Cf);
+        const float S = __fadd_ru(__fmul_ru(3.0f, __fmul_ru(oc, oc)), __fmul_ru(sc.any_Rf, sc.any_Rf));
+        const float g = __fsqrt_ru(__fmul_ru(40.0f * u, S));
+        a3 = __fmul_ru(__fadd_ru(__fmul_ru(3.0f, g), __fmul_ru(u, __fadd_ru(__fmul_ru(2.0f, __fadd_ru(sc.any_Cf, sc.any_Rf)), oc))), I);
+    }
+    s0f = __fmul_ru(4.0f, __fadd_ru(__fadd_ru(__fadd_ru(a0, a1), a2), a3));
+    s1f = __fmul_ru(4.0f, __fadd_ru(__fmul_ru(__fadd_ru(__fmul_ru(__fmul_ru(K, 6.0f), DE2), 5.0f * u), 1.3333334f), 8.0f * u));
     return s0f <= 3.0e38f && s1f <= 3.0e38f;
 }
 
@@ -1744,6 +1755,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     v.any_E = flat.any_E; v.any_A = flat.any_A;
     v.any_Ef = std::nextafter(static_cast<float>(flat.any_E), std::numeric_limits<float>::infinity());  // >= any_E
     v.any_Af = std::nextafter(static_cast<float>(flat.any_A), std::numeric_limits<float>::infinity());
+    v.any_Cf = std::nextafter(static_cast<float>(flat.any_C), std::numeric_limits<float>::infinity());
+    v.any_Rf = flat.any_spheres ? std::nextafter(static_cast<float>(flat.any_R), std::numeric_limits<float>::infinity()) : -1.0f;
     std::memcpy(v.bg_rgb, flat.background.rgb, sizeof v.bg_rgb);
     *out = ds;
     return RTP_OK;

@@ -346,10 +346,11 @@ static void build_wide(const std::vector<DNode>& bn, std::vector<DWide>* out_wid
 }
 
 // Scene-side preparation of the any-order walk (rtp_device.cu walker_step_any). Distance culling is exact only
-// with a bound on how far a triangle's computed t (hittable.rs:85-95) can fall below the computed slab entry of its own box;
-// that bound grows with the triangle's extent, so outsized triangles and all spheres (whose roots cancel catastrophically,
-// hittable.rs:44-47) are taken out of the culled set: they are the "big" primitives, tested for every ray before the walk.
-// More than kMaxBig of them, or a tree too deep for the shared-memory stack, and the scene keeps the in-order walk.
+// with a bound on how far a primitive's computed t (hittable.rs:51-57, 85-95) can fall below the computed slab entry of its own
+// box; that bound grows with the primitive's extent (a triangle's edges, a sphere's |o - c|^2 - r^2 cancellation), so the
+// outsized primitives of a scene - the ground sphere of the bunny scenes, a floor made of two huge triangles - are taken out
+// of the culled set: up to kMaxBig "big" primitives are exempt from distance culling and tested whenever the ray enters
+// their box. A tree too deep for the shared-memory stack, or irregular boxes, and the scene keeps the in-order walk.
 constexpr size_t kFreeTreeLeaves = 262144;  // scenes below this size get the second, order-free culling tree
 
 // children are appended after their parents (build_wide), so one backward sweep propagates "contains a big primitive" upwards
@@ -380,41 +381,46 @@ static void prepare_any_order(FlatScene* out) {
         const DPrim& p = out->prims[s];
         return std::fmax(p.bmax[0] - p.bmin[0], std::fmax(p.bmax[1] - p.bmin[1], p.bmax[2] - p.bmin[2]));
     };
-    std::vector<double> ext;
-    ext.reserve(n);
-    for (size_t s = 0; s < n; ++s) {
-        if (kind[s] == RTP_HITTABLE_SPHERE) {
-            if (out->n_big == kMaxBig) return;
-            out->big[out->n_big++] = static_cast<uint32_t>(s) | (static_cast<uint32_t>(RTP_HITTABLE_SPHERE) << 31);
-        } else {
-            ext.push_back(extent(s));
-        }
-    }
+    // outsized primitives: more than 16 times the median extent; the eight largest of them are "big"
+    std::vector<double> ext(n);
+    for (size_t s = 0; s < n; ++s) ext[s] = extent(s);
     std::vector<uint8_t> is_big(n, 0);
-    for (uint32_t b = 0; b < out->n_big; ++b) is_big[out->big[b] & 0x7FFFFFFFu] = 1;
-    if (!ext.empty()) {
+    {
         std::vector<double> tmp = ext;
         std::nth_element(tmp.begin(), tmp.begin() + tmp.size() / 2, tmp.end());
         const double cap = 16.0 * tmp[tmp.size() / 2];
-        // the largest triangles above the cap, as many as fit
         std::vector<std::pair<double, uint32_t>> over;
         for (size_t s = 0; s < n; ++s)
-            if (kind[s] != RTP_HITTABLE_SPHERE && extent(s) > cap) over.push_back({extent(s), static_cast<uint32_t>(s)});
+            if (ext[s] > cap) over.push_back({ext[s], static_cast<uint32_t>(s)});
         std::sort(over.begin(), over.end(), [](const auto& a, const auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
         for (size_t k = 0; k < over.size() && out->n_big < kMaxBig; ++k) {
-            out->big[out->n_big++] = over[k].second | (static_cast<uint32_t>(RTP_HITTABLE_TRIANGLE) << 31);
+            out->big[out->n_big++] = over[k].second | (static_cast<uint32_t>(kind[over[k].second]) << 31);
             is_big[over[k].second] = 1;
         }
     }
-    double E = 0.0, A = 0.0;
+    // scene constants of the slack bound (rtp_device.cu any_slack): triangles E, A; spheres C (largest |centre coordinate|, bounded
+    // by the box planes) and R (largest radius) - over the primitives that are not big
+    double E = 0.0, A = 0.0, Cs = 0.0, Rs = 0.0;
+    bool spheres = false;
     for (size_t s = 0; s < n; ++s) {
         if (is_big[s]) continue;
         const DPrim& p = out->prims[s];
-        E = std::fmax(E, extent(s));
-        for (int k = 0; k < 3; ++k) A = std::fmax(A, std::fmax(std::fabs(p.bmin[k]), std::fabs(p.bmax[k])));
+        double mag = 0.0;
+        for (int k = 0; k < 3; ++k) mag = std::fmax(mag, std::fmax(std::fabs(p.bmin[k]), std::fabs(p.bmax[k])));
+        if (kind[s] == RTP_HITTABLE_SPHERE) {
+            spheres = true;
+            Cs = std::fmax(Cs, mag);
+            Rs = std::fmax(Rs, 0.5 * ext[s]);
+        } else {
+            E = std::fmax(E, ext[s]);
+            A = std::fmax(A, mag);
+        }
     }
     out->any_E = E * (1.0 + 1e-12);
     out->any_A = A * (1.0 + 1e-12);
+    out->any_spheres = spheres;
+    out->any_C = Cs * (1.0 + 1e-12);
+    out->any_R = Rs * (1.0 + 1e-12);
     mark_big(out->wide, is_big);
     out->any_ok = true;
 

@@ -118,6 +118,7 @@ struct DSceneView {  // passed by value to kernels
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
     float any_Ef, any_Af;  // the same, rounded up to f32
+    float any_Cf, any_Rf;  // spheres that are not big: largest |centre coordinate| and radius, rounded up; any_Rf < 0: there are none
 };
 constexpr uint32_t kMaxBig = 8;
 
@@ -145,7 +146,8 @@ struct FlatScene {
     uint32_t free_depth = 0;
     uint32_t n_big = 0;
     uint32_t big[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double any_E = 0.0, any_A = 0.0;
+    double any_E = 0.0, any_A = 0.0, any_C = 0.0, any_R = 0.0;
+    bool any_spheres = false;        // some sphere is not big: the slack bound needs the sphere term
     double scene_mag = 0.0;    // largest |coordinate| of any node box
     bool boxes_finite = true;  // every box is finite and ordered (min <= max): precondition of the sign-selected slab test, of the
                                // f32 culling walk and of re-shaping the tree; otherwise the reference topology and the literal test are used

@@ -203,9 +203,11 @@ def test_traversal_plan_of_scenes():
     assert (info.any_order, info.n_big) == (1, 1)  # the ground sphere
     assert 0 < info.culling_depth <= 16 and 0 < info.free_tree_depth <= 16
     _, info = api.bvh_build_order(scenes.demo())
-    assert (info.any_order, info.n_big) == (1, 3)  # earth, light and ground spheres
+    assert (info.any_order, info.n_big) == (1, 2)  # the ground and earth spheres dwarf the triangles; the small light sphere does not
     _, info = api.bvh_build_order(scenes.two_balls())
-    assert (info.any_order, info.n_big) == (1, 2)
+    assert (info.any_order, info.n_big) == (1, 0)  # two equal spheres: neither is outsized, the sphere term of the slack covers them
+    _, info = api.bvh_build_order(scenes.more_balls_optimized())
+    assert (info.any_order, info.n_big, info.n_leaves) == (1, 1, 3786)  # only the r = 1000 ground
     _, info = api.bvh_build_order(scenes.three_balls())  # a List root has no culling tree
     assert (info.any_order, info.culling_depth, info.free_tree_depth) == (0, 0, 0)
 
@@ -214,11 +216,9 @@ def test_traversal_plan_of_scenes():
     def scene_of(hittables, meshes=()):
         return api.ExampleScene(scenes._bunny_camera(), api.SceneData(mats, [], list(meshes)), "bvh", hittables, api.Emit.SkyGradient)
 
-    nine = api.Hittable.concat([api.Hittable.Sphere([x, 0.0, 0.0], 0.4, 0) for x in range(9)])
-    _, info = api.bvh_build_order(scene_of(nine))  # more exempt primitives than the walk allows: the scene keeps the in-order walk
-    assert info.any_order == 0
-    eight = api.Hittable.concat([api.Hittable.Sphere([x, 0.0, 0.0], 0.4, 0) for x in range(8)])
-    _, info = api.bvh_build_order(scene_of(eight))
+    many = api.Hittable.concat([api.Hittable.Sphere([x, 0.0, 0.0], 0.4, 0) for x in range(40)] +
+                               [api.Hittable.Sphere([3.0 * x, 50.0, 0.0], 20.0 + x, 0) for x in range(12)])
+    _, info = api.bvh_build_order(scene_of(many))  # twelve outsized spheres: the eight largest are exempt, the others widen the slack
     assert (info.any_order, info.n_big) == (1, 8)
     inverted = api.Hittable.concat([api.Hittable.Sphere([0.0, 0.0, 0.0], -0.5, 0), api.Hittable.Sphere([2.0, 0.0, 0.0], 0.5, 0)])
     _, info = api.bvh_build_order(scene_of(inverted))  # an inverted leaf box: reference topology, literal slab test, in-order walk

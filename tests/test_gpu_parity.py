@@ -938,3 +938,69 @@ def test_any_order_walk_unusual_rays(gpu, monkeypatch, name):
         g.close()
     assert (want["leaf"] != MISS).mean() > 0.3
     orc.close()
+
+
+@pytest.mark.parametrize("name", ["more_balls_optimized", "two_balls", "earth", "one_triangle", "sphere_soup"])
+def test_any_order_walk_on_sphere_scenes(gpu, monkeypatch, name):
+    """spheres that are not outsized stay in the culled set, covered by the sphere term of the slack bound (any_slack): sphere-heavy
+    scenes walked front to back must return the in-order bits, from outside, from inside the geometry and with grazing rays"""
+    import torch
+
+    rng = np.random.default_rng(31)
+    if name == "sphere_soup":  # overlapping, nested and touching spheres of very different sizes, duplicates included
+        n = 600
+        c = rng.uniform(-6, 6, (n, 3))
+        r = np.exp(rng.uniform(np.log(0.02), np.log(1.5), n))
+        parts = [api.Hittable.Sphere(c[k], float(r[k]), k % 3) for k in range(n)] + [api.Hittable.Sphere(c[k], float(r[k]), 1) for k in range(0, n, 7)]
+        mats = [api.Material.new(api.Scatter.Lambert, api.Absorb.WhiteBody, api.Emit.NONE), api.Material.new(api.Scatter.Metal(0.2), api.Absorb.WhiteBody, api.Emit.NONE),
+                api.Material.new(api.Scatter.Dielectric(1.5), api.Absorb.WhiteBody, api.Emit.NONE)]
+        sc = api.ExampleScene(scenes._bunny_camera(), api.SceneData(mats, [], []), "bvh", api.Hittable.concat(parts), api.Emit.SkyGradient)
+        centres, radii, reach = c, r, 8.0
+    else:
+        sc = getattr(scenes, name)()
+        sph = sc.hittables[sc.hittables["kind"] == A.HITTABLE_SPHERE]
+        small = sph[sph["radius"] < 100.0] if (sph["radius"] < 100.0).any() else sph
+        centres, radii, reach = small["center"], small["radius"], float(np.abs(small["center"]).max() + small["radius"].max() + 2.0)
+    cam = api.Camera(1.0, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+    m = 30000
+    rays = np.zeros(m, dtype=A.RAY_DTYPE)
+    o = rng.normal(size=(m, 3))
+    o = o / np.linalg.norm(o, axis=1, keepdims=True) * rng.uniform(0.2, 1.0, (m, 1)) * reach
+    o[:, 1] = np.abs(o[:, 1]) + 0.05
+    pick = rng.integers(0, len(centres), m)
+    # aim at a sphere, half of the rays at its silhouette (grazing: delta ~ 0)
+    tgt = centres[pick] + rng.normal(size=(m, 3)) * radii[pick][:, None] * 0.6
+    side = rng.normal(size=(m, 3))
+    to_c = centres[pick] - o
+    side -= (side * to_c).sum(axis=1, keepdims=True) * to_c / (to_c * to_c).sum(axis=1, keepdims=True)
+    side /= np.linalg.norm(side, axis=1, keepdims=True)
+    graze = centres[pick] + side * radii[pick][:, None] * (1.0 + rng.choice([0.0, 1e-15, -1e-15, 1e-9, -1e-9, 1e-4], m))[:, None]
+    tgt[m // 2:] = graze[m // 2:]
+    d = tgt - o
+    rays["origin"], rays["direction"] = o, d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["t_min"], rays["t_max"] = 1e-3, np.inf
+    rays = np.concatenate([oracle.camera_rays(cam, 160, 160), rays])
+    orc = oracle.Scene(sc)
+    want = orc.hit(rays)
+    d_rays = torch.from_numpy(rays.view(np.float64).reshape(-1, 8)).cuda()
+    d_hits = torch.empty((len(rays), 2), dtype=torch.float64, device="cuda")
+    visits = {}
+    for order in ("inorder", "any"):
+        monkeypatch.setenv("RTP_TRAVERSAL", order)
+        g = api.Scene(sc)
+        assert g.info().any_order == (0 if order == "inorder" else 1)
+        st = g.hit_device_counted(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+        assert_hits_equal_bits(d_hits.cpu().numpy().view(A.HIT_DTYPE).reshape(-1), want)
+        assert st.conservative_violations == 0
+        assert st.order_rewalks <= len(rays) // 200, st.order_rewalks
+        visits[order] = st.node_visits
+        if order == "any":
+            ig, fg, sg = g.render(96, 96, 2, seed=6)
+            io, fo, so = orc.render(96, 96, 2, seed=6)
+            rep = image_report(ig, io)
+            assert rep["rmse"] <= IMG_RMSE and rep["differing"] <= max(1, IMG_FRAC * rep["pixels"]), rep
+        g.close()
+    if name in ("more_balls_optimized", "sphere_soup"):
+        assert visits["any"] < visits["inorder"], visits
+    assert (want["leaf"] != MISS).mean() > 0.3
+    orc.close()
