@@ -549,10 +549,11 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
 // hit distance and m_p = max(t_p, computed slab entry of p's own box) — both independent of T. A leaf is NORMAL when
 // m_p = t_p and ABNORMAL when rounding put t_p below its own box entry. If every leaf with t_p <= M + 2 slack is normal, where
 // M is the smallest m_p, the process returns min t_p, ties to the larger DFS rank — no matter in which order the leaves are
-// looked at. slack(t) bounds m_p - t_p for every triangle that is not "big" (error analysis of hittable.rs:77-95 in DESIGN.md
-// §4b), so a box whose conservative entry lies above T_win = t_best + 2 slack(t_best) holds no leaf that can matter and is
-// skipped, children are visited nearest first, and the primitive tests use T_win as their upper bound. Big primitives (spheres,
-// outsized triangles) are tested for every ray before the walk. A ray that met an abnormal leaf inside the final window is
+// looked at. slack(t) bounds m_p - t_p for every primitive that is not "big" (error analysis of hittable.rs:39-57, 77-95 in
+// DESIGN.md §4b), so a box whose conservative entry lies above T_win = t_best + 2 slack(t_best) holds no leaf that can matter and
+// is skipped, children are visited nearest first, and the primitive tests use T_win as their upper bound. Big primitives (the
+// outsized ones of a scene, at most eight) are exempt from the window: a child that is or contains one is tested against the
+// ray's own t_max, visited first and never dropped. A ray that met an abnormal leaf inside the final window is
 // walked again in the reference's order (walker_step_wide): exactness never rests on the bound being tight, only on it
 // being a bound.
 // ---------------------------------------------------------------------------------------------

@@ -113,7 +113,7 @@ struct DSceneView {  // passed by value to kernels
     // still tested and the rare ray whose answer could depend on the reference's visiting order is re-walked in order
     uint32_t any_order;    // 1: eligible rays of this scene use it
     uint32_t any_cap;      // entries of the per-lane any-order stack
-    uint32_t n_big;        // primitives exempt from distance culling (all spheres, outsized triangles), at most kMaxBig
+    uint32_t n_big;        // primitives exempt from distance culling (the outsized ones: extent above 16x the median), at most kMaxBig
     uint32_t _pad_any;
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
