@@ -49,6 +49,25 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_local_cores(local_rank):
+    """One process per GPU: run this rank (and first-touch its pinned host buffers) on the cores NVML reports as local to its
+    GPU, so that the host side of the e2e leg does not cross the socket interconnect. Returns the number of cores, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def c2_scene_and_camera(scenes, api):
     """bunny scene (example_scenes.rs:309-350 with a Lambert bunny) and its camera at 1920x1080, lens 0"""
     sc = scenes.bunny_lambert()
@@ -160,6 +179,7 @@ def main():
     rank, local_rank, world = dist_env()
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    affinity = bind_to_gpu_local_cores(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     api.init(local_rank)
     if world > 1:
@@ -330,6 +350,7 @@ def main():
             "workload": WORKLOAD,
             "rays_per_step_per_gpu": N_RAYS, "sharding": "rank r traces sub-sample r of a world-times supersampled primary batch; no data-path collective",
             "l2": "inputs larger than L2: two 132.7 MB ray buffers are rotated between steps (265 MB > 126 MB L2); no flush needed",
+            "host_cores_bound_per_rank": affinity,
         },
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * RAY_BYTES, "d2h_bytes_per_step": N_RAYS * HIT_BYTES,
                 "steps": e2e_steps, "api": "rtp_trace_closest (pinned host buffers, 256Ki-ray chunks on 3 streams)", "gpu_launches_per_step": e2e_launches,
