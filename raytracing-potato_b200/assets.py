@@ -1,7 +1,7 @@
 """Scene inputs: the reference's meshes/texture (from the committed fixture) and the synthetic sky.
 
-The GPU box has no /root/reference, so the reference assets travel as a compressed fixture,
-tests/golden/assets.npz, written by tests/golden/make_fixtures.py from
+The GPU box has no /root/reference, so the reference assets travel as package data,
+raytracing-potato_b200/data/assets.npz, written by tests/golden/make_fixtures.py from
 /root/reference/assets/{bunny.obj,bunny_flat.obj,earthmap.tga}. `assets/sky_panorama.tga` is absent
 from the reference checkout (.MISSING_LARGE_BLOBS), so the sky is generated here with integer
 arithmetic only — identical bytes on every machine.
@@ -15,8 +15,7 @@ import numpy as np
 from . import _abi as A
 from .api import Mesh
 
-REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FIXTURE = os.path.join(REPO_ROOT, "tests", "golden", "assets.npz")
+FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "assets.npz")
 _cache = {}
 
 

@@ -421,6 +421,13 @@ struct WorkQueue {
     unsigned int _pad;
 };
 
+// Rays the pure any-order kernel (trace_any_kernel) does not answer itself: not eligible for the f32 walk, stack overflow, or an
+// abnormal leaf inside the final window. The in-order kernel traces them in a second launch (its `index` mode).
+struct DeferList {
+    uint32_t* idx;               // ray indices handed to the in-order kernel
+    unsigned long long* count;   // entries in idx (device); reset by the in-order launch that consumes it
+};
+
 struct Tuning {
     int refill_min;  // refill when at least this many lanes are empty
     int prim_batch;  // run primitive tests when at least this many lanes are parked at a leaf
@@ -531,7 +538,7 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
     const uint32_t s1 = (k & 1u) << 5;  // clamped funnel shifts pick one of four 32-bit words
     const uint32_t c = __funnelshift_rc(__funnelshift_rc(w.c0, w.c1, s1), __funnelshift_rc(w.c2, w.c3, s1), (k & 2u) << 4);
     const bool is_leaf = (c & kWideLeaf) != 0u;
-    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & kWideSlotMask);
     const bool first = w.prim == kNoPrim;
     w.prim2 = (is_leaf & !first) ? leaf : w.prim2;
     w.prim = (is_leaf & first) ? leaf : w.prim;
@@ -638,7 +645,7 @@ __device__ __forceinline__ void any_begin(Walker& w, const DSceneView& sc, Local
 // hand a child word to the lane: a leaf is parked (oldest pending leaf first), an internal child becomes the node to visit; selects only
 __device__ __forceinline__ void any_take(Walker& w, uint32_t c) {
     const bool is_leaf = (c & kWideLeaf) != 0u;
-    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & 0x3FFFFFFFu);
+    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & kWideSlotMask);
     const bool first = w.prim == kNoPrim;
     w.prim2 = (is_leaf & !first) ? leaf : w.prim2;
     w.prim = (is_leaf & first) ? leaf : w.prim;
@@ -1279,9 +1286,10 @@ constexpr int kTraceBlocksPerSM = 6;
 template <bool COUNT, int OUT, bool LIST, int ANY>
 __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (ANY == 1 ? 5 : kTraceBlocksPerSM))) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev,
-                                                                  TailArgs ta) {
+                                                                  TailArgs ta, DeferList index) {
     extern __shared__ __align__(16) uint32_t wide_stack[];  // [level][thread]; any-order lanes: [entry][thread] of uint2
     if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
+    if (index.idx) n = static_cast<size_t>(*index.count);  // index mode: trace rays[index.idx[q]] for q < *index.count (deferred by trace_any_kernel)
     if (OUT == OUT_TAIL) {
         if (n == 0 || n > ta.threshold) return;  // the trace/shade pair that follows handles this queue
         rays = ta.q.rays[ta.bounce & 1u];
@@ -1397,8 +1405,9 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
             if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
             if (is_empty) {
                 const int rank = __popc(empty & lt_mask);
-                const size_t i = static_cast<size_t>(base) + rank;
-                if (rank < cnt && i < n) {
+                const size_t q = static_cast<size_t>(base) + rank;
+                if (rank < cnt && q < n) {
+                    const size_t i = index.idx ? static_cast<size_t>(index.idx[q]) : q;
                     idx = i;
                     const double2* rp = reinterpret_cast<const double2*>(rays + i);
                     const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
@@ -1460,6 +1469,311 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
             wq->next = 0ull;
             wq->done_blocks = 0u;
             if (OUT == OUT_TAIL) ta.q.count[ta.bounce] = 0ull;  // every path is finished: the launches that follow find empty queues
+            if (index.idx) *index.count = 0ull;                 // the deferred rays are done: rearm the list for the next launch
+            __threadfence();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pure any-order traversal kernel. Same walk and the same exactness argument as walker_step_any / any_test
+// above, rebuilt around what the profile of the combined kernel showed (profiles/r01_trace_any_c2.md: 14 % of the executed
+// instructions were register moves at loop heads, 19 % branch / reconvergence / predicate set-up, 12 % the slab arithmetic):
+//   * one loop with one back edge; lane state is a handful of scalars (node, stack top as a shared-memory ADDRESS, two pending
+//     leaf words), no struct passed by reference through inlined functions with early returns;
+//   * only any-order lanes live here. A ray that is not eligible (axis-parallel, non-finite, huge coordinates, t_min < 0), whose
+//     stack would overflow, or whose answer may depend on the reference's visiting order (abnormal leaf inside the final
+//     window) is appended to a DEFER list and traced by a second launch of the in-order kernel (trace_persistent_kernel with an
+//     index list), so neither the in-order walker nor the exact f64 walker is compiled into this kernel;
+//   * the scene's big primitives (at most eight) are tested when the ray starts, with all lanes of the refill together, instead
+//     of travelling through the tree as window-exempt children: the step carries no big-mask load and no per-child selects,
+//     and the walk starts with the window already closed to the nearest big hit. Testing them first is the same sequential
+//     process (the claim in DESIGN.md 4b does not depend on the order in which leaves are looked at); a big leaf met again in
+//     the tree is skipped (kWideBig);
+//   * rays are read with ld.global.nc.L1::no_allocate and results written with st.global.cs: the 80 B/ray stream does not
+//     displace the culling tree from L1.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+constexpr uint32_t kAnyStride = 128u * 8u;  // bytes between two levels of a thread's stack column ([entry][thread] of uint2)
+
+// per-ray slack coefficients from scalars; false: not eligible
+__device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D3 inv, double tmin, float& s0f, float& s1f) {
+    const float u = 0x1.0p-53f, K = 8.9e-9f;
+    const float Po = __double2float_ru(fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z)));
+    const float P = __fadd_ru(Po, sc.any_Af);
+    const float D = __double2float_ru(fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z)));
+    const float I = __double2float_ru(fmax(fmax(fabs(inv.x), fabs(inv.y)), fabs(inv.z)));
+    const float E = sc.any_Ef;
+    const float E2 = __fmul_ru(E, E), DE2 = __fmul_ru(D, E2), PE = __fmul_ru(P, E);
+    const float kappa = __fmul_ru(__fmul_ru(K, 6.0f), DE2);
+    const float e_uv = __fadd_ru(__fmul_ru(K, __fadd_ru(__fmul_ru(6.0f, __fmul_ru(PE, D)), __fmul_ru(6.06f, DE2))), 3.0f * u);
+    const float eta = __fmul_ru(__fadd_ru(__fmul_ru(4.0f, e_uv), 5.0f * u), E);
+    const float a0 = __fmul_ru(__fmul_ru(__fadd_ru(eta, __fmul_ru(u, P)), I), 1.0000002f);
+    const float a1 = __fmul_ru(__fmul_ru(__fmul_ru(K, 6.0f), __fmul_ru(PE, E)), 1.3333334f);
+    const float a2 = __fmul_ru(3.0f * u, __double2float_ru(fabs(tmin)));
+    float a3 = 0.f;
+    if (sc.any_Rf >= 0.f) {  // scene-uniform branch
+        const float oc = __fadd_ru(Po, sc.any_Cf);
+        const float S = __fadd_ru(__fmul_ru(3.0f, __fmul_ru(oc, oc)), __fmul_ru(sc.any_Rf, sc.any_Rf));
+        const float g = __fsqrt_ru(__fmul_ru(40.0f * u, S));
+        a3 = __fmul_ru(__fadd_ru(__fmul_ru(3.0f, g), __fmul_ru(u, __fadd_ru(__fmul_ru(2.0f, __fadd_ru(sc.any_Cf, sc.any_Rf)), oc))), I);
+    }
+    s0f = __fmul_ru(4.0f, __fadd_ru(__fadd_ru(__fadd_ru(a0, a1), a2), a3));
+    s1f = __fmul_ru(4.0f, __fadd_ru(__fmul_ru(__fadd_ru(__fmul_ru(__fmul_ru(K, 6.0f), DE2), 5.0f * u), 1.3333334f), 8.0f * u));
+    return (kappa <= 0.25f) & (e_uv <= 0.01f) & (s0f <= 3.0e38f) & (s1f <= 3.0e38f);
+}
+
+#ifndef RTP_ANY_BLOCKS
+#define RTP_ANY_BLOCKS 5  // resident blocks per SM the kernel is built for (register budget 65536 / (128 x blocks))
+#endif
+#ifndef RTP_ANY_STEPS
+#define RTP_ANY_STEPS 2   // walk steps per round of votes
+#endif
+template <bool COUNT, int OUT>
+__global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out, Counters* counters,
+                                                           WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev, DeferList defer) {
+    extern __shared__ __align__(16) uint32_t any_stack[];
+    if (n_dev) n = static_cast<size_t>(*n_dev);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t sbase = smem_u32(any_stack) + threadIdx.x * 8u;      // bottom of this thread's stack column
+    const uint32_t slimit = sbase + (sc.any_cap - 3u) * kAnyStride;     // pushing three more entries above this would overflow
+    LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
+
+    // ---- lane state -----------------------------------------------------------------------------------------------------------
+    D3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
+    double tmin = 0.0;
+    double best_t = 0.0, best_u = 0.0, best_v = 0.0;  // closest normal hit so far (valid when best != kNoPrim)
+    uint32_t best = kNoPrim;                          // slot | kind << 31
+    double T_win = 0.0;                               // window top: min(ray.t_max, best_t + 2 slack(best_t))
+    float A_min = CUDART_INF_F;                       // smallest t of an abnormal leaf seen (rounded DOWN to f32: conservative)
+    float s0f = 0.f, s1f = 0.f;
+    float ix = 0.f, iy = 0.f, iz = 0.f, clx = 0.f, cly = 0.f, clz = 0.f, chx = 0.f, chy = 0.f, chz = 0.f, tmin_dn = 0.f, T_up = 0.f;
+    uint32_t onx = 0, ony = 2, onz = 4, ofx = 1, ofy = 3, ofz = 5;  // float4 index of the near / far plane of each axis inside a node (DWide::plane)
+    bool sx = false, sy = false, sz = false;
+    uint32_t node = kNone;        // node to visit next, or kNone: take the next stack entry
+    uint32_t sp = sbase;          // shared-memory address of the first free entry of this thread's column
+    uint32_t leaf0 = 0u, leaf1 = 0u;  // pending leaves (raw child words, oldest first); 0 = none (child word 0 is the root, never a leaf)
+    uint32_t idx = 0xFFFFFFFFu;   // ray held by this lane (index into rays / out), 0xFFFFFFFF = none
+    bool more = true;             // warp-uniform: the queue may still hold rays
+    const size_t n_warps = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
+    const int lane_cap = static_cast<int>(min(static_cast<size_t>(32), max(static_cast<size_t>(tune.min_lanes), (n + n_warps - 1) / n_warps)));
+    const int refill_thr = min(tune.refill_min, max(1, lane_cap / 2));
+    const float4* __restrict__ tree = reinterpret_cast<const float4*>(sc.any_wide);  // a node = 8 float4: 32-bit indexing (device_scene_upload: < 2^29 nodes)
+
+    // exact test of one leaf in any-order mode (any_test above, on this kernel's scalars)
+    auto test_leaf = [&](uint32_t cw) {
+        const uint32_t slot = cw & kWideSlotMask, kind = (cw >> 30) & 1u;
+        const DPrim* p = sc.prims + slot;
+        double t, u = 0.0, v = 0.0;
+        bool hit;
+        if (kind == RTP_HITTABLE_TRIANGLE) {
+            if (COUNT) lc.triangle_tests++;
+            hit = test_triangle(p, o, d, tmin, T_win, t, u, v);
+        } else {
+            if (COUNT) lc.sphere_tests++;
+            hit = test_sphere(p, o, d, tmin, T_win, t);
+        }
+        if (hit) {
+            if (!(t == t)) {
+                A_min = -CUDART_INF_F;  // NaN t (overflowing geometry): let the in-order walk decide
+            } else {
+                const double* pb = p->bmin;
+                const double2 b0 = ldg2(pb), b1 = ldg2(pb + 2), b2 = ldg2(pb + 4);
+                if (COUNT) lc.leaf_gates++;
+                if (collide_fast(b0, b1, b2, o, inv, sx, sy, sz, tmin, t)) {
+                    // normal leaf: min t, ties to the larger DFS rank (= slot)
+                    const uint32_t bslot = best & 0x7FFFFFFFu;
+                    if (best == kNoPrim || t < best_t || (t == best_t && slot > bslot)) {
+                        best_t = t; best_u = u; best_v = v; best = slot | (kind << 31);
+                        const double win = t + 2.0 * (static_cast<double>(s0f) + static_cast<double>(s1f) * fabs(t));
+                        T_win = fmin(T_win, win);
+                        T_up = __double2float_ru(T_win);
+                    }
+                } else if (collide_fast(b0, b1, b2, o, inv, sx, sy, sz, tmin, CUDART_INF)) {
+                    A_min = fminf(A_min, __double2float_rd(t));  // abnormal: its box is entered, but only after t
+                }
+            }
+        }
+    };
+
+    for (;;) {
+        // ---- retire finished rays and refill ------------------------------------------------------------------------------
+        const bool walking0 = (node != kNone) | (sp != sbase);
+        const bool busy = walking0 | (leaf0 != 0u);
+        const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);
+        const int n_busy = __popc(busy_mask);
+        const int room = min(32 - n_busy, max(lane_cap - n_busy, 0));
+        if (busy_mask == 0u || (more && room >= refill_thr)) {
+            if (!busy && idx != 0xFFFFFFFFu) {
+                // the walk of this lane's ray is over. An abnormal leaf inside the final window: the answer may depend on the
+                // reference's visiting order, the in-order kernel decides (A_min was rounded down, T_win compared in f64: conservative)
+                if (A_min != CUDART_INF_F && static_cast<double>(A_min) <= T_win) {
+                    const unsigned long long slot = atomicAdd(defer.count, 1ull);
+                    defer.idx[slot] = idx;
+                    if (COUNT) lc.rewalks++;
+                } else {
+                    HitRec h;
+                    h.t = best_t; h.u = best_u; h.v = best_v; h.slot = best == kNoPrim ? kNoPrim : (best & 0x7FFFFFFFu); h.kind = best >> 31;
+                    write_hit<OUT>(sc, out, idx, o, d, h);
+                }
+                idx = 0xFFFFFFFFu;
+            }
+            if (!more) {
+                if (busy_mask == 0u) break;
+            } else {
+                const unsigned free_mask = ~busy_mask;
+                const int cnt = room, leader = __ffs(free_mask) - 1;
+                unsigned long long base = 0;
+                if (static_cast<int>(lane) == leader) base = atomicAdd(&wq->next, static_cast<unsigned long long>(cnt));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
+                const int rank = __popc(free_mask & lt_mask);
+                const size_t i = static_cast<size_t>(base) + rank;
+                if (!busy && rank < cnt && i < n) {
+                    const double* rp = reinterpret_cast<const double*>(rays + i);
+                    const double2 r0 = ldg_stream2(rp), r1 = ldg_stream2(rp + 2), r2 = ldg_stream2(rp + 4), r3 = ldg_stream2(rp + 6);
+                    o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
+                    tmin = r3.x;
+                    const double tmax = r3.y;
+                    inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
+                    lc.rays++;
+                    // eligibility (walker_start + any_begin): finite origin, 1e-15 <= |1/d| <= 1e15 on every axis, |o| <= 1e15,
+                    // 0 <= t_min <= t_max, self-consistent slack
+                    bool ok = in_f32_range(inv.x) & in_f32_range(inv.y) & in_f32_range(inv.z) & (fabs(o.x) <= 1e15) & (fabs(o.y) <= 1e15) &
+                              (fabs(o.z) <= 1e15) & (tmax >= tmin) & (tmin >= 0.0);
+                    ok = ok & any_slack_of(sc, o, d, inv, tmin, s0f, s1f);
+                    if (!ok) {
+                        const unsigned long long slot = atomicAdd(defer.count, 1ull);
+                        defer.idx[slot] = static_cast<uint32_t>(i);
+                    } else {
+                        idx = static_cast<uint32_t>(i);
+                        sx = inv.x < 0.0; sy = inv.y < 0.0; sz = inv.z < 0.0;
+                        const double px = o.x * inv.x, py = o.y * inv.y, pz = o.z * inv.z;
+                        const double kx = fabs(px) * 0x1.0p-21 + 1e-37, ky = fabs(py) * 0x1.0p-21 + 1e-37, kz = fabs(pz) * 0x1.0p-21 + 1e-37;
+                        ix = __double2float_rn(inv.x); iy = __double2float_rn(inv.y); iz = __double2float_rn(inv.z);
+                        clx = __double2float_rd(-px - kx); cly = __double2float_rd(-py - ky); clz = __double2float_rd(-pz - kz);
+                        chx = __double2float_ru(-px + kx); chy = __double2float_ru(-py + ky); chz = __double2float_ru(-pz + kz);
+                        tmin_dn = __double2float_rd(tmin);
+                        onx = sx ? 1u : 0u; ony = sy ? 3u : 2u; onz = sz ? 5u : 4u;
+                        ofx = sx ? 0u : 1u; ofy = sy ? 2u : 3u; ofz = sz ? 4u : 5u;
+                        best = kNoPrim; best_t = tmax; best_u = 0.0; best_v = 0.0;
+                        T_win = tmax; T_up = __double2float_ru(tmax);
+                        A_min = CUDART_INF_F;
+                        leaf0 = 0u; leaf1 = 0u; sp = sbase;
+                        node = 0u;
+                        // the big primitives first, all lanes of the refill together
+                        for (uint32_t k = 0; k < sc.n_big; ++k) test_leaf(kWideLeaf | ((sc.big[k] >> 31) << 30) | (sc.big[k] & kWideSlotMask));
+                    }
+                }
+            }
+        }
+
+        // ---- walk: up to two steps per round ----------------------------------------------------------------------------------
+#pragma unroll
+        for (int rep = 0; rep < RTP_ANY_STEPS; ++rep) {
+            if ((leaf1 == 0u) & ((node != kNone) | (sp != sbase))) {
+                if (node == kNone) {
+                    sp -= kAnyStride;
+                    const uint2 e = lds_v2(sp);
+                    if (__uint_as_float(e.y) <= T_up) {  // else: the window shrank since this entry was postponed
+                        if (e.x & kWideLeaf) {
+                            if (leaf0 == 0u) leaf0 = e.x; else leaf1 = e.x;
+                        } else {
+                            node = e.x;
+                        }
+                    }
+                }
+                if (node != kNone) {
+                    const uint32_t nb = node * 8u;
+                    const float4 nx4 = __ldg(tree + (nb + onx));
+                    const float4 ny4 = __ldg(tree + (nb + ony));
+                    const float4 nz4 = __ldg(tree + (nb + onz));
+                    const float4 fx4 = __ldg(tree + (nb + ofx));
+                    const float4 fy4 = __ldg(tree + (nb + ofy));
+                    const float4 fz4 = __ldg(tree + (nb + ofz));
+                    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(tree + (nb + 6u)));
+                    // key = conservative entry distance (non-negative float: its bits order like the value) with the child index in the
+                    // two low bits; a child that is missed, beyond the window or empty gets the largest key
+#define RTP_KEY(c, idx_)                                                                                                            \
+    const float n##c = fmaxf(fmaxf(fmaf(nx4.c, ix, clx), fmaf(ny4.c, iy, cly)), fmaxf(fmaf(nz4.c, iz, clz), tmin_dn));               \
+    const float f##c = fminf(fminf(fmaf(fx4.c, ix, chx), fmaf(fy4.c, iy, chy)), fminf(fmaf(fz4.c, iz, chz), T_up));                  \
+    const uint32_t k##c = f##c >= n##c ? ((__float_as_uint(n##c) & ~3u) | idx_) : 0xFFFFFFFFu;
+                    RTP_KEY(x, 0u) RTP_KEY(y, 1u) RTP_KEY(z, 2u) RTP_KEY(w, 3u)
+#undef RTP_KEY
+                    if (COUNT) {
+                        lc.node_visits++;
+                        const double* b64 = sc.any_boxes + static_cast<size_t>(node) * 24;
+                        const uint32_t keys[4] = {kx, ky, kz, kw};
+                        for (uint32_t k = 0; k < 4; ++k)  // a rejected child must fail the exact test with the window top as t_max
+                            if (keys[k] == 0xFFFFFFFFu && (&ch.x)[k] != kWideEmpty &&
+                                collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), o, inv, tmin, T_win))
+                                lc.violations++;
+                    }
+                    const uint32_t a0 = min(kx, ky), a1 = max(kx, ky), b0 = min(kz, kw), b1 = max(kz, kw);
+                    uint32_t s0 = min(a0, b0);
+                    const uint32_t m0 = max(a0, b0), m1 = min(a1, b1), s3 = max(a1, b1);
+                    const uint32_t s1 = min(m0, m1), s2 = max(m0, m1);
+#define RTP_SEL(k) (((k) & 2u) ? (((k) & 1u) ? ch.w : ch.z) : (((k) & 1u) ? ch.y : ch.x))
+                    node = kNone;
+                    if (s1 != 0xFFFFFFFFu) {  // the keys are sorted: without a second child there is no third or fourth
+                        if (sp > slimit) {
+                            // no room to postpone three children: give the ray to the in-order kernel
+                            A_min = -CUDART_INF_F; sp = sbase; leaf0 = 0u; leaf1 = 0u; s0 = 0xFFFFFFFFu;
+                        } else {
+                            if (s2 != 0xFFFFFFFFu) {
+                                if (s3 != 0xFFFFFFFFu) { sts_v2(sp, RTP_SEL(s3), s3 & ~3u); sp += kAnyStride; }
+                                sts_v2(sp, RTP_SEL(s2), s2 & ~3u); sp += kAnyStride;
+                            }
+                            sts_v2(sp, RTP_SEL(s1), s1 & ~3u); sp += kAnyStride;
+                        }
+                    }
+                    if (s0 != 0xFFFFFFFFu) {
+                        const uint32_t c = RTP_SEL(s0);
+                        if (c & kWideLeaf) {
+                            if (leaf0 == 0u) leaf0 = c; else leaf1 = c;
+                        } else {
+                            node = c;
+                        }
+                    }
+#undef RTP_SEL
+                }
+            }
+        }
+
+        // ---- leaves: when enough lanes hold one, or nobody can walk ----------------------------------------------------------
+        const unsigned parked = __ballot_sync(0xffffffffu, leaf0 != 0u);
+        if (parked != 0u) {
+            const unsigned walking = __ballot_sync(0xffffffffu, (leaf1 == 0u) & ((node != kNone) | (sp != sbase)));
+            if (__popc(parked) >= tune.prim_batch || walking == 0u) {
+                if (leaf0 != 0u) {
+                    if (!(leaf0 & kWideBig)) test_leaf(leaf0);  // big primitives were tested when the ray started
+                    leaf0 = leaf1;
+                    leaf1 = 0u;
+                }
+            }
+        }
+    }
+
+    flush_counters<COUNT>(counters, lc);
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(&wq->done_blocks, 1u) == static_cast<unsigned>(n_warps) - 1u) {
+            wq->next = 0ull;
+            wq->done_blocks = 0u;
             __threadfence();
         }
     }
@@ -1555,6 +1869,7 @@ __global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ 
 constexpr int kPipeDepth = 3;
 constexpr size_t kAnyOrderBigScene = 262144;  // leaves from which the 4-blocks-per-SM variant is used
 constexpr unsigned kQueueSlots = 64;
+constexpr unsigned kLaunchSlots = 8;
 static size_t chunk_rays() {  // rays per pipeline stage: 2^18 (16 MiB of rays) unless RTP_CHUNK_LOG2 says otherwise (tuning runs)
     static const size_t v = [] { const char* e = std::getenv("RTP_CHUNK_LOG2"); const int l = e ? std::atoi(e) : 18; return size_t(1) << std::max(10, std::min(24, l)); }();
     return v;
@@ -1579,9 +1894,28 @@ struct DeviceScene {
 
     std::mutex lock;  // serialises calls that use the scratch below
     Counters* counters = nullptr;
-    WorkQueue* queues = nullptr;       // kQueueSlots self-rearming work queues, handed out round-robin per launch
-    std::atomic<unsigned> queue_seq{0};  // launches from several host threads never share a slot unless > kQueueSlots are in flight
-    int persistent_blocks = 0;         // grid of the persistent kernels: SM count x resident blocks per SM
+    // Per-launch device state of the persistent kernels: a self-rearming work queue and the defer list of trace_any_kernel.
+    // Slots are handed out round-robin; each remembers the last launch that used it through an event, and the next user's
+    // stream waits on that event first, so two launches in flight on different streams never share a queue or a list.
+    struct LaunchSlot {
+        WorkQueue* wq = nullptr;
+        unsigned long long* defer_count = nullptr;
+        uint32_t* defer_idx = nullptr;
+        size_t defer_cap = 0;
+        cudaEvent_t last_use = nullptr;
+        cudaStream_t stream = nullptr;  // stream of the last launch that used the slot
+        bool used = false;
+    };
+    LaunchSlot slots[kLaunchSlots];
+    std::mutex launch_lock;            // acquire slot + enqueue + record event is one critical section per launch
+    unsigned slot_seq = 0;
+    WorkQueue* queues = nullptr;       // backing store of the slots' queues and defer counters
+    int persistent_blocks = 0;         // grid of the in-order persistent kernel: SM count x resident blocks per SM
+    int inorder_blocks = 0, inorder_tail_blocks = 0;  // grids of the ANY = 0 build (persistent_blocks / tail_blocks are the combined kernel's when that is in use)
+    size_t inorder_stack_bytes = 0;
+    int any_blocks = 0;                // grid of trace_any_kernel
+    size_t any_stack_bytes = 0;        // its dynamic shared memory: any_cap x 128 threads x 8 B
+    bool use_combined = false;         // RTP_TRACE_KERNEL=combined: the round-1 kernel with both walkers compiled in (A/B runs)
     int any_order = 0;                 // 1, 2: eligible rays take the any-order walk (RTP_TRAVERSAL), kernel variant ANY = 1 or 2
     uint32_t any_cap = 0;              // any-order stack entries per lane
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
@@ -1621,6 +1955,10 @@ void device_scene_free(DeviceScene* ds) {
     for (uint8_t* p : ds->images) cudaFree(p);
     cudaFree(ds->counters);
     cudaFree(ds->queues);
+    for (DeviceScene::LaunchSlot& sl : ds->slots) {
+        cudaFree(sl.defer_idx);
+        if (sl.last_use) cudaEventDestroy(sl.last_use);
+    }
     for (int k = 0; k < kPipeDepth; ++k) {
         if (ds->streams[k]) cudaStreamDestroy(ds->streams[k]);
         cudaFree(ds->stage_rays[k]); cudaFree(ds->stage_hits[k]);
@@ -1663,7 +2001,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     {
         // RTP_TRAVERSAL=any | inorder overrides the choice
         const char* tv = std::getenv("RTP_TRAVERSAL");
-        const bool f32_ok = flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96;
+        const bool f32_ok = flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96 &&
+                            flat.wide.size() < (size_t(1) << 28) && flat.free_wide.size() < (size_t(1) << 28);  // trace_any_kernel indexes nodes as 32-bit float4 offsets
         bool want = true;  // every eligible scene takes the any-order walk by default (measured faster from the 4,969-leaf bunny up)
         if (tv && std::string(tv) == "any") want = true;
         if (tv && std::string(tv) == "inorder") want = false;
@@ -1689,28 +2028,47 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ds->counters), sizeof(Counters));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ds->queues), kQueueSlots * sizeof(WorkQueue));
     if (e == cudaSuccess) e = cudaMemset(ds->queues, 0, kQueueSlots * sizeof(WorkQueue));
+    for (unsigned k = 0; k < kLaunchSlots && e == cudaSuccess; ++k) {
+        // queue entry 2k: the slot's work queue; entry 2k + 1: its defer counter (first 8 bytes)
+        ds->slots[k].wq = ds->queues + 2 * k;
+        ds->slots[k].defer_count = reinterpret_cast<unsigned long long*>(ds->queues + 2 * k + 1);
+        e = cudaEventCreateWithFlags(&ds->slots[k].last_use, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, ds->device);
-        int per_sm = 0, tail_per_sm = 0;
+        int per_sm = 0, tail_per_sm = 0, any_per_sm = 0;
+        const char* env_k = std::getenv("RTP_TRACE_KERNEL");
+        ds->use_combined = env_k && std::string(env_k) == "combined";
+        // in-order kernel (every scene: List roots, scenes outside the any-order walk's preconditions, the rays trace_any_kernel
+        // defers, tail-mode launches): one stack word per tree level and thread
+        ds->inorder_stack_bytes = ds->stack_bytes;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 0>, 128, ds->inorder_stack_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 0>, 128, ds->inorder_stack_bytes);
+        ds->inorder_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
+        ds->inorder_tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (ds->any_order) {
-            // any-order lanes postpone up to three siblings per level, each with its entry distance: at most 3 x depth + 1 entries of
-            // 8 B per lane, capped at 32 (a lane that would need more hands its ray to the in-order walk, whose one-word entries
-            // live in the same column: at least `depth` slots)
+            // any-order lanes postpone up to three siblings per level, each with its entry distance (8 B): a primary ray of the bunny
+            // never holds more than 16 entries (gpurun_out/r2_sweep1.log: 0 overflows of 2 M rays at 16, 65 of 4 Mi incoherent ones),
+            // deep trees get up to 32; a lane that would need more defers its ray to the in-order kernel
             const uint32_t any_depth = ds->free_wide ? flat.free_depth : flat.wide_depth;
-            ds->any_cap = std::max<uint32_t>(flat.wide_depth, std::min<uint32_t>(3u * any_depth + 1u, 32u));
-            if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = std::max<uint32_t>(flat.wide_depth, static_cast<uint32_t>(std::max(1, std::min(48, std::atoi(v)))));  // tests
-            ds->stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
-            if (ds->any_order == 2) {
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 2>, 128, ds->stack_bytes);
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 2>, 128, ds->stack_bytes);
-            } else {
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 1>, 128, ds->stack_bytes);
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 1>, 128, ds->stack_bytes);
+            ds->any_cap = std::max<uint32_t>(4u, std::min<uint32_t>(3u * any_depth + 1u, any_depth <= 12 ? 20u : 32u));
+            if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = static_cast<uint32_t>(std::max(4, std::min(48, std::atoi(v))));  // tests
+            ds->any_stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&any_per_sm, trace_any_kernel<false, OUT_HIT>, 128, ds->any_stack_bytes);
+            ds->any_blocks = prop.multiProcessorCount * std::max(any_per_sm, 1);
+            if (ds->use_combined) {
+                // the round-1 kernel: in-order entries live in the .x halves of the same uint2 columns, at least `depth` of them
+                ds->any_cap = std::max<uint32_t>(flat.wide_depth, ds->any_cap);
+                ds->stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
+                if (ds->any_order == 2) {
+                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 2>, 128, ds->stack_bytes);
+                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 2>, 128, ds->stack_bytes);
+                } else {
+                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 1>, 128, ds->stack_bytes);
+                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 1>, 128, ds->stack_bytes);
+                }
             }
-        } else {
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 0>, 128, ds->stack_bytes);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 0>, 128, ds->stack_bytes);
         }
         size_t free_b = 0, total_b = 0;
         if (e == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
@@ -1719,7 +2077,8 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
         ds->shade_blocks = prop.multiProcessorCount * 3;
         if (const char* v = std::getenv("RTP_BUILD_TIMING")) if (std::atoi(v) != 0)
             std::fprintf(stderr, "[rtp build] 4-wide tree depth %u (order-free tree: %u), %s walk (%u big primitives), %zu B of stack per block, %d traversal blocks per SM\n",
-                         flat.wide_depth, flat.free_depth, ds->any_order ? "any-order" : "in-order", flat.n_big, ds->stack_bytes, per_sm);
+                         flat.wide_depth, flat.free_depth, ds->any_order ? (ds->use_combined ? "any-order (combined kernel)" : "any-order") : "in-order", flat.n_big,
+                         ds->any_order && !ds->use_combined ? ds->any_stack_bytes : ds->stack_bytes, ds->any_order && !ds->use_combined ? any_per_sm : per_sm);
         ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (const char* v = std::getenv("RTP_TAIL_THRESHOLD")) ds->tail_threshold = static_cast<uint32_t>(std::max(0l, std::atol(v)));
         if (const char* v = std::getenv("RTP_TAIL_OFFER")) ds->tail_offer = std::atoi(v) != 0;
@@ -1753,6 +2112,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     v.any_cap = ds->any_cap;
     v.n_big = flat.n_big;
     v._pad_any = 0;
+    for (int k = 0; k < 8; ++k) v.big[k] = flat.big[k];
     v.any_E = flat.any_E; v.any_A = flat.any_A;
     v.any_Ef = std::nextafter(static_cast<float>(flat.any_E), std::numeric_limits<float>::infinity());  // >= any_E
     v.any_Af = std::nextafter(static_cast<float>(flat.any_A), std::numeric_limits<float>::infinity());
@@ -1800,12 +2160,58 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
     } else {
         // persistent grid: a whole number of resident blocks per SM, never more warps than rays
         const size_t want = (n + 3) / 4;  // a warp per ray at least: small batches are latency-bound per warp, so they are spread thin
-        const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(out_mode == OUT_TAIL ? ds->tail_blocks : ds->persistent_blocks), want)));
-        WorkQueue* wq = ds->queues + (ds->queue_seq.fetch_add(1u) % kQueueSlots);
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
         const TailArgs ta = tail ? *tail : TailArgs{};
-        const int any = list ? 0 : ds->any_order;
-#define RTP_LAUNCH_PERSISTENT(C, O, L, A) trace_persistent_kernel<C, O, L, A><<<g, block, ds->stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta)
+        // which build: the pure any-order kernel + a deferred in-order launch (default for eligible scenes), the in-order kernel
+        // alone (List roots, scenes outside the preconditions, tail-mode launches), or round 1's combined kernel (A/B runs)
+        const bool pure_any = !list && ds->any_order && !ds->use_combined && out_mode != OUT_TAIL;
+        const int any = (list || !ds->use_combined) ? 0 : ds->any_order;
+        if (n > 0xFFFFFFFEull && pure_any) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
+
+        std::lock_guard<std::mutex> guard(ds->launch_lock);
+        // a stream keeps its slot (launches on one stream are ordered anyway, and the slot's defer list is already sized);
+        // a new stream takes an unused slot, or the next one round-robin after waiting for that slot's last launch
+        DeviceScene::LaunchSlot* pick = nullptr;
+        for (DeviceScene::LaunchSlot& sl : ds->slots)
+            if (sl.used && sl.stream == stream) { pick = &sl; break; }
+        if (!pick)
+            for (DeviceScene::LaunchSlot& sl : ds->slots)
+                if (!sl.used) { pick = &sl; break; }
+        if (!pick) {
+            pick = &ds->slots[ds->slot_seq++ % kLaunchSlots];
+            RTP_CUDA(cudaStreamWaitEvent(stream, pick->last_use, 0));  // its previous launch, on another stream, must be over
+        }
+        DeviceScene::LaunchSlot& slot = *pick;
+        if (pure_any && slot.defer_cap < n) {
+            if (slot.used) RTP_CUDA(cudaEventSynchronize(slot.last_use));
+            cudaFree(slot.defer_idx); slot.defer_idx = nullptr; slot.defer_cap = 0;
+            const size_t cap = std::max<size_t>(n, 65536);
+            RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&slot.defer_idx), cap * sizeof(uint32_t)));
+            slot.defer_cap = cap;
+        }
+        WorkQueue* wq = slot.wq;
+        const DeferList no_index{nullptr, nullptr};
+        if (pure_any) {
+            const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->any_blocks), want)));
+            const DeferList defer{slot.defer_idx, slot.defer_count};
+#define RTP_LAUNCH_ANY(C, O) trace_any_kernel<C, O><<<g, block, ds->any_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, defer)
+            if (out_mode == OUT_FULL) { if (count) RTP_LAUNCH_ANY(true, OUT_FULL); else RTP_LAUNCH_ANY(false, OUT_FULL); }
+            else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_ANY(true, OUT_WAVE); else RTP_LAUNCH_ANY(false, OUT_WAVE); }
+            else { if (count) RTP_LAUNCH_ANY(true, OUT_HIT); else RTP_LAUNCH_ANY(false, OUT_HIT); }
+#undef RTP_LAUNCH_ANY
+            RTP_CUDA(cudaGetLastError());
+            // the deferred rays (normally none: the launch then finds an empty list and leaves at once), in the reference's order
+            const dim3 g2(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->inorder_blocks), want)));
+#define RTP_LAUNCH_DEFERRED(C, O) trace_persistent_kernel<C, O, false, 0><<<g2, block, ds->inorder_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, nullptr, ta, defer)
+            if (out_mode == OUT_FULL) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_FULL); else RTP_LAUNCH_DEFERRED(false, OUT_FULL); }
+            else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_WAVE); else RTP_LAUNCH_DEFERRED(false, OUT_WAVE); }
+            else { if (count) RTP_LAUNCH_DEFERRED(true, OUT_HIT); else RTP_LAUNCH_DEFERRED(false, OUT_HIT); }
+#undef RTP_LAUNCH_DEFERRED
+        } else {
+            const int blocks = any ? (out_mode == OUT_TAIL ? ds->tail_blocks : ds->persistent_blocks) : (out_mode == OUT_TAIL ? ds->inorder_tail_blocks : ds->inorder_blocks);
+            const size_t smem = any ? ds->stack_bytes : ds->inorder_stack_bytes;
+            const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(blocks), want)));
+#define RTP_LAUNCH_PERSISTENT(C, O, L, A) trace_persistent_kernel<C, O, L, A><<<g, block, smem, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta, no_index)
 #define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
     do {                                                                                             \
         if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true, 0); else RTP_LAUNCH_PERSISTENT(false, O, true, 0); }     \
@@ -1813,12 +2219,18 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         else if (any == 1) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 1); else RTP_LAUNCH_PERSISTENT(false, O, false, 1); } \
         else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 0); else RTP_LAUNCH_PERSISTENT(false, O, false, 0); }        \
     } while (0)
-        if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
-        else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);
-        else if (out_mode == OUT_TAIL) RTP_LAUNCH_PERSISTENT_O(OUT_TAIL);
-        else RTP_LAUNCH_PERSISTENT_O(OUT_HIT);
+            if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
+            else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);
+            else if (out_mode == OUT_TAIL) RTP_LAUNCH_PERSISTENT_O(OUT_TAIL);
+            else RTP_LAUNCH_PERSISTENT_O(OUT_HIT);
 #undef RTP_LAUNCH_PERSISTENT_O
 #undef RTP_LAUNCH_PERSISTENT
+        }
+        RTP_CUDA(cudaGetLastError());
+        RTP_CUDA(cudaEventRecord(slot.last_use, stream));
+        slot.used = true;
+        slot.stream = stream;
+        return RTP_OK;
     }
     RTP_CUDA(cudaGetLastError());
     return RTP_OK;

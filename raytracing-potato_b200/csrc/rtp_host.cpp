@@ -362,8 +362,9 @@ static void mark_big(std::vector<DWide>& wide, const std::vector<uint8_t>& is_bi
         for (int k = 0; k < 4; ++k) {
             const uint32_t c = w.child[k];
             if (c == kWideEmpty) continue;
-            const bool big = (c & kWideLeaf) ? is_big[c & 0x3FFFFFFFu] != 0 : (c > i ? has_big[c] != 0 : true);
+            const bool big = (c & kWideLeaf) ? is_big[c & kWideSlotMask] != 0 : (c > i ? has_big[c] != 0 : true);
             if (big) w.big_mask |= 1u << k;
+            if (big && (c & kWideLeaf)) w.child[k] |= kWideBig;
         }
         has_big[i] = w.big_mask != 0;
     }
@@ -492,7 +493,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
         return set_error(RTP_ERR_INVALID, "null table with non-zero count");
     if (d->root_kind == RTP_ROOT_BVH && d->n_hittables == 0)
         return set_error(RTP_ERR_INVALID, "Bvh::new on an empty list is unreachable!() in the reference (bvh.rs:40)");
-    if (d->n_hittables >= 0x3FFFFFFFu) return set_error(RTP_ERR_INVALID, "too many hittables");
+    if (d->n_hittables >= kWideSlotMask) return set_error(RTP_ERR_INVALID, "too many hittables");
 
     const bool timing = std::getenv("RTP_BUILD_TIMING") != nullptr;  // phase times of the host build on stderr
     auto t0 = std::chrono::steady_clock::now();

@@ -54,8 +54,10 @@ static_assert(sizeof(DPrim) == 128, "DPrim must be 128 bytes");
 // the child's exact f64 box rounded OUTWARD and inflated by 2^-21 * max(|min|,|max|) per axis, so that an f32 slab
 // evaluation with the matching ray-side slack is a rigorous lower / upper bound of the reference's f64 evaluation
 // (rtp_device.cu collide32). child[k]: internal = index of the child node; leaf = kWideLeaf | kind << 30 |
-// primitive slot; unused = kWideEmpty with an inverted (+inf, -inf) box that no ray can enter.
+// kWideBig if big | primitive slot; unused = kWideEmpty with an inverted (+inf, -inf) box that no ray can enter.
 constexpr uint32_t kWideLeaf = 0x80000000u;
+constexpr uint32_t kWideBig = 0x20000000u;       // leaf child word: the primitive is one of the scene's big primitives (trace_any_kernel tests those up front)
+constexpr uint32_t kWideSlotMask = 0x1FFFFFFFu;  // leaf child word: primitive slot
 constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
 struct alignas(128) DWide {  // 128 B = one L1/L2 line
     float plane[3][2][4];    // [axis][0 = min, 1 = max][child]
@@ -115,6 +117,7 @@ struct DSceneView {  // passed by value to kernels
     uint32_t any_cap;      // entries of the per-lane any-order stack
     uint32_t n_big;        // primitives exempt from distance culling (the outsized ones: extent above 16x the median), at most kMaxBig
     uint32_t _pad_any;
+    uint32_t big[8];       // their slots | kind << 31
     double any_E;          // largest box extent of a triangle that is not big
     double any_A;          // largest |coordinate| of such a triangle
     float any_Ef, any_Af;  // the same, rounded up to f32

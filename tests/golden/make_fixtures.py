@@ -1,4 +1,5 @@
-"""Regenerates tests/golden/assets.npz from the reference checkout (run in the build container only).
+"""Regenerates raytracing-potato_b200/data/assets.npz (the scene inputs the package ships) from the reference checkout
+(run in the build container only).
 
     python tests/golden/make_fixtures.py
 
@@ -34,7 +35,7 @@ def main():
     assert (img[..., 3] == 255).all()
     out["earthmap_rgb"] = img[..., :3].copy()
     print("earthmap", img.shape)
-    path = os.path.join(HERE, "assets.npz")
+    path = os.path.join(os.path.dirname(os.path.dirname(HERE)), "raytracing-potato_b200", "data", "assets.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
