@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RTP_ABI_VERSION 2u
+#define RTP_ABI_VERSION 3u
 
 typedef enum rtp_status {
     RTP_OK = 0,
@@ -89,15 +89,21 @@ typedef struct rtp_mesh {
     uint32_t _pad;
 } rtp_mesh;
 
-/* hittable.rs:10-15 `Hittable`. Only the two primitive variants cross the boundary; the
- * container variants are expressed by rtp_scene_desc.root_kind. */
-typedef enum rtp_hittable_kind { RTP_HITTABLE_SPHERE = 0, RTP_HITTABLE_TRIANGLE = 1 } rtp_hittable_kind;
+/* hittable.rs:10-15 `Hittable`. The root container is expressed by rtp_scene_desc.root_kind; a container NESTED inside
+ * the root's list (hittable.rs:13-14: a `List` as a BVH leaf or list item, a `Bvh` as a list item) names a run of
+ * rtp_scene_desc.nested. Where the reference panics - a `Bvh` whose bounding box is needed, i.e. a `Bvh` below a `Bvh`
+ * (hittable.rs:32), an empty `Bvh` (bvh.rs:40) - rtp_scene_create returns RTP_ERR_INVALID. */
+typedef enum rtp_hittable_kind {
+    RTP_HITTABLE_SPHERE = 0, RTP_HITTABLE_TRIANGLE = 1,
+    RTP_HITTABLE_LIST = 2, /* Hittable::List(items): linear closest hit, later equal t wins (hittable.rs:110-120) */
+    RTP_HITTABLE_BVH = 3   /* Hittable::Bvh(Bvh::new(items)) (bvh.rs:70-91)                                    */
+} rtp_hittable_kind;
 
 typedef struct rtp_hittable {
     uint32_t kind;     /* rtp_hittable_kind                                              */
     uint32_t material; /* sphere: MaterialId. triangle: ignored (taken from the mesh)    */
-    uint32_t mesh;     /* triangle: MeshId                                               */
-    uint32_t triangle; /* triangle: TriangleId = index of its first entry in `indices`   */
+    uint32_t mesh;     /* triangle: MeshId.     list / bvh: index of its first item in rtp_scene_desc.nested */
+    uint32_t triangle; /* triangle: TriangleId = index of its first entry in `indices`. list / bvh: number of items */
     double center[3];  /* sphere                                                         */
     double radius;     /* sphere                                                         */
 } rtp_hittable;
@@ -171,6 +177,9 @@ typedef struct rtp_scene_desc {
     uint32_t n_materials;
     uint32_t n_textures;
     rtp_emit background;
+    const rtp_hittable* nested; /* items of nested List / Bvh hittables (may be NULL when n_nested == 0) */
+    uint32_t n_nested;
+    uint32_t _pad;
 } rtp_scene_desc;
 
 /* render.rs:19-25 `Camera` + utility.rs:160-163 `Transformation`.
@@ -199,7 +208,12 @@ typedef struct rtp_render_params {
     uint32_t tile_w;        /* Tile::width;  0 = full frame                                */
     uint32_t tile_h;        /* Tile::height; 0 = full frame                                */
     uint32_t flags;         /* RTP_RENDER_* */
-    uint32_t _pad;
+    uint32_t device_mask;   /* rtp_render / rtp_render_srgb8 on a scene made by rtp_scene_create_multi: bit d = device d takes part.
+                               0 = every device of the scene. The rows of the tile rectangle are dealt out to the devices
+                               round-robin and each device writes its rows straight into the host frame: no collective,
+                               pixels bit-identical to a one-device render (main.rs:46-98 fans out to its workers the same way) */
+    uint32_t row_offset;    /* with row_stride > 1: this call renders only rows tile_y + row_offset + k * row_stride of the    */
+    uint32_t row_stride;    /*   tile rectangle (one process per GPU splitting a frame by rows); 0 or 1 = every row          */
 } rtp_render_params;
 
 #define RTP_RENDER_RAW_SUMS 1u /* write Σ over the sample range instead of Σ / num_samples   */
@@ -217,6 +231,8 @@ typedef struct rtp_stats {
     double device_ms;       /* CUDA-event time of the device work of this call             */
     uint64_t kernel_launches;
     uint64_t order_rewalks; /* any-order walk: rays walked again in the reference's order (counting kernels only) */
+    double trace_ms;        /* render calls: CUDA-event time spent in the traversal kernel launches                */
+    double shade_ms;        /* render calls: ... in the generate / shade / resolve / output launches              */
 } rtp_stats;
 
 typedef struct rtp_scene_info {
@@ -288,6 +304,13 @@ int rtp_split_in_tiles(uint32_t full_width, uint32_t full_height, uint32_t tile_
  * (bvh.rs:36-91; centroid ties broken by LeafId), flattens it into the device
  * node/primitive layout and uploads everything to the current device. */
 int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out);
+/* The same scene replicated on every device of `device_mask` (bit d = CUDA device d; every one must be compute capability
+ * 10.x). The description is flattened once and uploaded to each device. rtp_render / rtp_render_srgb8 then split a frame
+ * by rows over the devices, rtp_trace_closest* / rtp_trace_camera deal their chunks out to them; the *_device entry points
+ * use the first device of the mask. This is the reference's one-call-site fan-out (main.rs:46-98) across GPUs. */
+int rtp_scene_create_multi(const rtp_scene_desc* desc, uint32_t device_mask, rtp_scene** out);
+/* bit d set = the scene holds a replica on device d */
+int rtp_scene_devices(const rtp_scene* scene, uint32_t* device_mask_out);
 void rtp_scene_destroy(rtp_scene* scene);
 int rtp_scene_get_info(const rtp_scene* scene, rtp_scene_info* info);
 /* Leaf ids in the reference's depth-first left-to-right order (n_leaves entries). */

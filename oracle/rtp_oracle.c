@@ -876,7 +876,10 @@ static void* render_worker(void* arg) {
         if (job->n_tiles == 0) { pthread_mutex_unlock(&job->lock); break; }
         memcpy(tile, job->tiles + 4 * (--job->n_tiles), sizeof tile); /* pop() from the end */
         pthread_mutex_unlock(&job->lock);
-        for (uint32_t tj = 0; tj < tile[3]; ++tj)
+        for (uint32_t tj = 0; tj < tile[3]; ++tj) {
+            /* rtp_render_params.row_offset / row_stride: only rows tile_y + row_offset + k * row_stride belong to this call */
+            const uint32_t rs = p->row_stride ? p->row_stride : 1u, rel = tj + tile[1] - p->tile_y;
+            if (rel < p->row_offset || (rel - p->row_offset) % rs != 0) continue;
             for (uint32_t ti = 0; ti < tile[2]; ++ti) {
                 uint32_t i = ti + tile[0], j = tj + tile[1];
                 v3 final_color = v3_make(0, 0, 0);
@@ -899,6 +902,7 @@ static void* render_worker(void* arg) {
                 job->rgb[3 * px + 2] = final_color.z;
                 if (job->fg) job->fg[px] = foreground;
             }
+        }
     }
     pthread_mutex_lock(&job->lock);
     job->total.rays += c.rays; job->total.node_visits += c.node_visits;

@@ -10,13 +10,13 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MISS = 0xFFFFFFFF
 
 # rtp_status
 OK, ERR_INVALID, ERR_IO, ERR_FORMAT, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 # rtp_hittable_kind
-HITTABLE_SPHERE, HITTABLE_TRIANGLE = 0, 1
+HITTABLE_SPHERE, HITTABLE_TRIANGLE, HITTABLE_LIST, HITTABLE_BVH = 0, 1, 2, 3
 # rtp_scatter_kind / rtp_absorb_kind / rtp_emit_kind / rtp_texture_kind / rtp_root_kind
 SCATTER_NONE, SCATTER_LAMBERT, SCATTER_METAL, SCATTER_DIELECTRIC = 0, 1, 2, 3
 ABSORB_BLACKBODY, ABSORB_WHITEBODY, ABSORB_ALBEDO, ABSORB_ALBEDO_MAP = 0, 1, 2, 3
@@ -94,6 +94,9 @@ class SceneDesc(C.Structure):
         ("n_materials", C.c_uint32),
         ("n_textures", C.c_uint32),
         ("background", Emit),
+        ("nested", C.c_void_p),
+        ("n_nested", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 
@@ -122,7 +125,9 @@ class RenderParams(C.Structure):
         ("tile_w", C.c_uint32),
         ("tile_h", C.c_uint32),
         ("flags", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("device_mask", C.c_uint32),
+        ("row_offset", C.c_uint32),
+        ("row_stride", C.c_uint32),
     ]
 
 
@@ -138,6 +143,8 @@ class Stats(C.Structure):
         ("device_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
         ("order_rewalks", C.c_uint64),
+        ("trace_ms", C.c_double),
+        ("shade_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -180,6 +187,8 @@ PROTOTYPES = {
     "rtp_frame_to_srgb8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "rtp_split_in_tiles": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, _P(C.c_size_t)]),
     "rtp_scene_create": (C.c_int, [_P(SceneDesc), _P(C.c_void_p)]),
+    "rtp_scene_create_multi": (C.c_int, [_P(SceneDesc), C.c_uint32, _P(C.c_void_p)]),
+    "rtp_scene_devices": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
     "rtp_scene_destroy": (None, [C.c_void_p]),
     "rtp_scene_get_info": (C.c_int, [C.c_void_p, _P(SceneInfo)]),
     "rtp_bvh_build_order": (C.c_int, [_P(SceneDesc), C.c_void_p, C.c_size_t, _P(SceneInfo)]),

@@ -341,6 +341,33 @@ class Hittable:
         return np.concatenate(list(parts)) if len(parts) else np.zeros(0, dtype=A.HITTABLE_DTYPE)
 
 
+class NestedPool:
+    """Items of nested containers (`Hittable::List(vec)` / `Hittable::Bvh(Bvh::new(vec))` used as an item of another
+    container, hittable.rs:13-14). `List(items)` / `Bvh(items)` store the items in the pool and return the one-element
+    hittable that names them; hand `pool.array()` to ExampleScene(nested=...)."""
+
+    def __init__(self):
+        self._parts: List[np.ndarray] = []
+        self._n = 0
+
+    def _add(self, kind: int, items: np.ndarray) -> np.ndarray:
+        items = np.ascontiguousarray(items, dtype=A.HITTABLE_DTYPE)
+        h = np.zeros(1, dtype=A.HITTABLE_DTYPE)
+        h["kind"], h["mesh"], h["triangle"] = kind, self._n, len(items)
+        self._parts.append(items)
+        self._n += len(items)
+        return h
+
+    def List(self, items: np.ndarray) -> np.ndarray:
+        return self._add(A.HITTABLE_LIST, items)
+
+    def Bvh(self, items: np.ndarray) -> np.ndarray:
+        return self._add(A.HITTABLE_BVH, items)
+
+    def array(self) -> np.ndarray:
+        return Hittable.concat(self._parts)
+
+
 @dataclass
 class SceneData:
     """render.rs:10-14"""
@@ -359,6 +386,7 @@ class ExampleScene:
     root_kind: str
     hittables: np.ndarray
     background: Emit
+    nested: Optional[np.ndarray] = None  # items of nested List / Bvh hittables (NestedPool.array())
 
 
 def build_desc(scene: ExampleScene):
@@ -393,7 +421,8 @@ def build_desc(scene: ExampleScene):
             c.rgba = img.ctypes.data
         texs[i] = c
     hit = np.ascontiguousarray(scene.hittables, dtype=A.HITTABLE_DTYPE)
-    keep += [meshes, mats, texs, hit]
+    nested = np.ascontiguousarray(scene.nested if scene.nested is not None else np.zeros(0, dtype=A.HITTABLE_DTYPE), dtype=A.HITTABLE_DTYPE)
+    keep += [meshes, mats, texs, hit, nested]
     d = A.SceneDesc()
     d.abi_version = A.ABI_VERSION
     d.root_kind = {"bvh": A.ROOT_BVH, "list": A.ROOT_LIST}[scene.root_kind]
@@ -404,11 +433,18 @@ def build_desc(scene: ExampleScene):
     d.n_meshes, d.n_hittables = len(sd.mesh_table), len(hit)
     d.n_materials, d.n_textures = len(sd.material_table), len(sd.texture_table)
     d.background = scene.background.to_c()
+    d.nested = nested.ctypes.data if len(nested) else None
+    d.n_nested = len(nested)
     return d, keep
 
 
-def render_params(width, height, num_samples, max_bounce=8, seed=1, sample_begin=0, sample_end=None, tile=None, flags=0) -> A.RenderParams:
+def render_params(width, height, num_samples, max_bounce=8, seed=1, sample_begin=0, sample_end=None, tile=None, flags=0,
+                  rows=None, device_mask=0) -> A.RenderParams:
+    """rows = (row_offset, row_stride): only every row_stride-th row of the tile rectangle, starting at row_offset"""
     p = A.RenderParams()
+    if rows is not None:
+        p.row_offset, p.row_stride = rows
+    p.device_mask = device_mask
     p.width, p.height, p.num_samples, p.max_bounce, p.seed = width, height, num_samples, max_bounce, seed
     p.sample_begin = sample_begin
     p.sample_end = num_samples if sample_end is None else sample_end
@@ -474,11 +510,15 @@ class PinnedBuffer:
 class Scene:
     """Device-resident scene: the replacement for `ExampleScene.root` + `scene_data` + `background`."""
 
-    def __init__(self, scene: ExampleScene):
+    def __init__(self, scene: ExampleScene, device_mask: int = 0):
+        """device_mask != 0: replicate the scene on those CUDA devices (rtp_scene_create_multi); render() / hit() then fan out"""
         self._lib = A.load()
         desc, keep = build_desc(scene)
         h = C.c_void_p()
-        _check(self._lib, self._lib.rtp_scene_create(C.byref(desc), C.byref(h)))
+        if device_mask:
+            _check(self._lib, self._lib.rtp_scene_create_multi(C.byref(desc), device_mask, C.byref(h)))
+        else:
+            _check(self._lib, self._lib.rtp_scene_create(C.byref(desc), C.byref(h)))
         del keep
         self._h = h
         self.camera = scene.camera
@@ -503,6 +543,12 @@ class Scene:
     @property
     def handle(self):
         return self._h
+
+    def devices(self) -> int:
+        """bit d set = the scene holds a replica on CUDA device d"""
+        m = C.c_uint32(0)
+        _check(self._lib, self._lib.rtp_scene_devices(self._h, C.byref(m)))
+        return m.value
 
     def info(self) -> A.SceneInfo:
         i = A.SceneInfo()
@@ -547,24 +593,28 @@ class Scene:
 
     # -- main.rs:61-92 --
     def render(self, width: int, height: int, num_samples: int, max_bounce: int = 8, seed: int = 1, camera: Optional[Camera] = None,
-               sample_range=None, tile=None, flags: int = 0, out: Optional[np.ndarray] = None, foreground: bool = True):
+               sample_range=None, tile=None, flags: int = 0, out=None, foreground: bool = True, rows=None, device_mask: int = 0):
+        """out: an [h, w, 3] f64 array, or a pair (rgb [h, w, 3], foreground [h, w] or None) of caller buffers (e.g. pinned)"""
         cam = camera or self.camera
         cam = Camera(width / height, cam.fov, cam.focal_dist, cam.lens_radius, cam.transformation)  # main.rs:22 overrides the aspect
         p = render_params(width, height, num_samples, max_bounce, seed,
-                          sample_range[0] if sample_range else 0, sample_range[1] if sample_range else None, tile, flags)
-        rgbf = out if out is not None else np.zeros((height, width, 3), dtype=np.float64)
-        fg = np.zeros((height, width), dtype=np.float64) if foreground else None
+                          sample_range[0] if sample_range else 0, sample_range[1] if sample_range else None, tile, flags, rows, device_mask)
+        if isinstance(out, tuple):
+            rgbf, fg = out
+        else:
+            rgbf = out if out is not None else np.zeros((height, width, 3), dtype=np.float64)
+            fg = np.zeros((height, width), dtype=np.float64) if foreground else None
         st = A.Stats()
         cc = cam.to_c()
         _check(self._lib, self._lib.rtp_render(self._h, C.byref(cc), C.byref(p), A.ptr(rgbf), A.ptr(fg) if fg is not None else None, C.byref(st)))
         return rgbf, fg, st
 
     def render_srgb8(self, width: int, height: int, num_samples: int, max_bounce: int = 8, seed: int = 1, camera: Optional[Camera] = None,
-                     tile=None, transparent_background: bool = False, out: Optional[np.ndarray] = None):
+                     tile=None, transparent_background: bool = False, out: Optional[np.ndarray] = None, rows=None, device_mask: int = 0):
         """main.rs:61-122: render + tile merge + to_srgb_u8 with the output stage on the device; [height, width, 4] uint8, ready for tga.save"""
         cam = camera or self.camera
         cam = Camera(width / height, cam.fov, cam.focal_dist, cam.lens_radius, cam.transformation)
-        p = render_params(width, height, num_samples, max_bounce, seed, 0, None, tile, A.RENDER_TRANSPARENT if transparent_background else 0)
+        p = render_params(width, height, num_samples, max_bounce, seed, 0, None, tile, A.RENDER_TRANSPARENT if transparent_background else 0, rows, device_mask)
         rgba = out if out is not None else np.zeros((height, width, 4), dtype=np.uint8)
         st = A.Stats()
         cc = cam.to_c()

@@ -1004,6 +1004,8 @@ struct DRender {
     uint32_t tile_x, tile_y, tile_w, tile_h;
     uint32_t sample_begin;  // first sample of this launch
     uint32_t n_samples;     // samples per pixel in this launch
+    uint32_t row_offset;    // this launch covers rows tile_y + row_offset + k * row_stride, k < tile_h (rtp_render_params.row_*:
+    uint32_t row_stride;    //   a frame split by rows over devices or processes); tile_h counts the rows of THIS launch
     uint32_t _pad;
     unsigned long long seed;
 };
@@ -1014,7 +1016,7 @@ __device__ __forceinline__ void path_coords(const DRender& rp, size_t p, uint32_
     const size_t pix = p / rp.n_samples;
     smp = rp.sample_begin + static_cast<uint32_t>(p % rp.n_samples);
     i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
-    j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+    j = rp.tile_y + rp.row_offset + static_cast<uint32_t>(pix / rp.tile_w) * rp.row_stride;
 }
 
 // main.rs:70-76: jittered uv (render.rs:76-81), lens sample (render.rs:36, drawn even when lens_radius == 0), Camera::shoot
@@ -1813,7 +1815,7 @@ __global__ void __launch_bounds__(256) write_frame_kernel(const double4* __restr
     const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
     const uint32_t i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
-    const uint32_t j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+    const uint32_t j = rp.tile_y + rp.row_offset + static_cast<uint32_t>(pix / rp.tile_w) * rp.row_stride;
     const size_t px = static_cast<size_t>(i) + static_cast<size_t>(j) * rp.width;
     double4 a = acc[pix];
     if (divisor != 0.0) { a.x = a.x / divisor; a.y = a.y / divisor; a.z = a.z / divisor; a.w = a.w / divisor; }
@@ -1839,7 +1841,7 @@ __global__ void __launch_bounds__(256) srgb8_kernel(const double4* __restrict__ 
     const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
     const uint32_t i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
-    const uint32_t j = rp.tile_y + static_cast<uint32_t>(pix / rp.tile_w);
+    const uint32_t j = rp.tile_y + rp.row_offset + static_cast<uint32_t>(pix / rp.tile_w) * rp.row_stride;
     const size_t px = static_cast<size_t>(i) + static_cast<size_t>(j) * rp.width;
     double4 a = acc[pix];
     if (divisor != 0.0) { a.x = a.x / divisor; a.y = a.y / divisor; a.z = a.z / divisor; a.w = a.w / divisor; }
@@ -1922,6 +1924,13 @@ struct DeviceScene {
     Tuning tune{16, 6, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t render_done = nullptr; // end of the last render enqueued: the next render (any stream) waits for it before it
+    bool render_pending = false;       //   touches the per-scene scratch (queues, accumulators, counters)
+    std::vector<cudaEvent_t> ev_pool;  // render calls with stats: marks around the traversal launches (trace_ms / shade_ms)
+    size_t ev_used = 0;
+    size_t last_trace_launches = 1;    // kernels the last launch_trace call queued (2 with the deferred in-order launch)
+    size_t pending_launches = 0;       // of the render enqueued last (render_enqueue -> render_finish)
+    uint64_t pending_paths = 0;
     rtp_ray* stage_rays[kPipeDepth] = {nullptr, nullptr, nullptr};
     void* stage_hits[kPipeDepth] = {nullptr, nullptr, nullptr};
     double4* scratch = nullptr; size_t scratch_elems = 0;
@@ -1938,6 +1947,7 @@ struct DeviceScene {
     double* frame = nullptr; size_t frame_elems = 0;
     uchar4* frame8 = nullptr; size_t frame8_elems = 0;  // RGBA8 output stage
     SrgbFix* fixes = nullptr; unsigned int* n_fixes = nullptr;
+    unsigned int n_fix_host = 0;       // n_fixes of the last rtp_render_srgb8, copied back with the frame
 };
 
 template <class T>
@@ -1965,6 +1975,8 @@ void device_scene_free(DeviceScene* ds) {
     }
     if (ds->ev_begin) cudaEventDestroy(ds->ev_begin);
     if (ds->ev_end) cudaEventDestroy(ds->ev_end);
+    for (cudaEvent_t ev : ds->ev_pool) cudaEventDestroy(ev);
+    if (ds->render_done) cudaEventDestroy(ds->render_done);
     cudaFree(ds->scratch); cudaFree(ds->acc); cudaFree(ds->frame); cudaFree(ds->frame8); cudaFree(ds->fixes); cudaFree(ds->n_fixes);
     cudaFree(ds->wave.rays[0]); cudaFree(ds->wave.rays[1]); cudaFree(ds->wave.state[0]); cudaFree(ds->wave.state[1]);
     cudaFree(ds->wave.hits); cudaFree(ds->wave.stack); cudaFree(ds->wave.count);
@@ -1982,11 +1994,28 @@ static int require_device() {
 
 int ensure_device() { return require_device(); }
 
-int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
-    int rc = require_device();
+static int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(RTP_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                           " (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return set_error(RTP_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    RTP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return set_error(RTP_ERR_CUDA, std::string("device ") + prop.name + " is not compute capability 10.x; kernels are built for sm_100a only");
+    return RTP_OK;
+}
+
+int current_device() { return g_device; }
+
+int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
+    int rc = device < 0 ? require_device() : check_device(device);
     if (rc != RTP_OK) return rc;
+    if (device < 0) device = g_device;
+    RTP_CUDA(cudaSetDevice(device));
     DeviceScene* ds = new DeviceScene();
-    ds->device = g_device;
+    ds->device = device;
     auto bail = [&](int code) { device_scene_free(ds); return code; };
     if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide, &ds->wide, &ds->bytes)) != RTP_OK) return bail(rc);
@@ -2098,6 +2127,7 @@ int device_scene_upload(const FlatScene& flat, DeviceScene** out) {
     for (int k = 0; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&ds->streams[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_begin);
     if (e == cudaSuccess) e = cudaEventCreate(&ds->ev_end);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ds->render_done, cudaEventDisableTiming);
     if (e != cudaSuccess) return bail(set_error(RTP_ERR_CUDA, std::string("scene resources: ") + cudaGetErrorString(e)));
 
     DSceneView& v = ds->view;
@@ -2146,6 +2176,7 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
                         cudaStream_t stream, const unsigned long long* n_dev = nullptr, const TailArgs* tail = nullptr) {
     if (n == 0) return RTP_OK;
     const unsigned block = 128;
+    ds->last_trace_launches = 1;
     if (ds->use_simple_kernel && !n_dev && out_mode != OUT_WAVE) {
         const size_t grid = (n + block - 1) / block;
         if (grid > 0x7FFFFFFFull) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
@@ -2207,6 +2238,7 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
             else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_WAVE); else RTP_LAUNCH_DEFERRED(false, OUT_WAVE); }
             else { if (count) RTP_LAUNCH_DEFERRED(true, OUT_HIT); else RTP_LAUNCH_DEFERRED(false, OUT_HIT); }
 #undef RTP_LAUNCH_DEFERRED
+            ds->last_trace_launches = 2;
         } else {
             const int blocks = any ? (out_mode == OUT_TAIL ? ds->tail_blocks : ds->persistent_blocks) : (out_mode == OUT_TAIL ? ds->inorder_tail_blocks : ds->inorder_blocks);
             const size_t smem = any ? ds->stack_bytes : ds->inorder_stack_bytes;
@@ -2236,58 +2268,81 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
     return RTP_OK;
 }
 
-// Host-buffer batch: chunks flow H2D → kernel → D2H on kPipeDepth streams so copies overlap traversal.
+// Host-buffer batch: chunks flow H2D → kernel → D2H on kPipeDepth streams per device so copies overlap traversal; a scene that
+// lives on several devices (rtp_scene_create_multi) deals its chunks out to them round-robin, so every device's host link carries
+// a share of the 80 B/ray stream. Chunks are independent: no exchange between devices.
 // `camera` != nullptr: the rays are pixel-centre camera rays generated on the device chunk by chunk (rtp_trace_camera)
 static int trace_host(rtp_scene* scene, const rtp_ray* rays, size_t n, void* hits_out, bool full, rtp_stats* stats, const DCamera* camera = nullptr,
                       uint32_t width = 0, uint32_t height = 0) {
-    DeviceScene* ds = scene->dev;
-    std::lock_guard<std::mutex> guard(ds->lock);
-    RTP_CUDA(cudaSetDevice(ds->device));
+    const std::vector<DeviceScene*>& devs = scene->devs;
+    const size_t N = devs.size();
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (DeviceScene* ds : devs) locks.emplace_back(ds->lock);
     const size_t hit_bytes = full ? sizeof(rtp_hit_full) : sizeof(rtp_hit);
-    for (int k = 0; k < kPipeDepth; ++k) {
-        if (!ds->stage_rays[k]) RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->stage_rays[k]), kChunkRays * sizeof(rtp_ray)));
-        if (!ds->stage_hits[k]) RTP_CUDA(cudaMalloc(&ds->stage_hits[k], kChunkRays * sizeof(rtp_hit_full)));
-    }
     const bool count = stats != nullptr;
-    if (count) RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), ds->streams[0]));
-    RTP_CUDA(cudaEventRecord(ds->ev_begin, ds->streams[0]));
-    for (int k = 1; k < kPipeDepth; ++k) RTP_CUDA(cudaStreamWaitEvent(ds->streams[k], ds->ev_begin, 0));
-    size_t launches = 0, chunk_id = 0;
-    for (size_t off = 0; off < n; off += kChunkRays, ++chunk_id) {
-        const size_t m = std::min(kChunkRays, n - off);
-        const int k = static_cast<int>(chunk_id % kPipeDepth);
-        cudaStream_t st = ds->streams[k];
-        if (camera) {
-            camera_rays_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(*camera, width, height, ds->stage_rays[k], off, m);
-            RTP_CUDA(cudaGetLastError());
-            ++launches;
-        } else {
-            RTP_CUDA(cudaMemcpyAsync(ds->stage_rays[k], rays + off, m * sizeof(rtp_ray), cudaMemcpyHostToDevice, st));
+    const size_t n_chunks = (n + kChunkRays - 1) / kChunkRays;
+    const size_t used = std::min(N, n_chunks);  // devices that get at least one chunk
+    int rc = RTP_OK;
+    for (size_t d = 0; d < used && rc == RTP_OK; ++d) {
+        DeviceScene* ds = devs[d];
+        RTP_CUDA(cudaSetDevice(ds->device));
+        for (int k = 0; k < kPipeDepth; ++k) {
+            if (!ds->stage_rays[k]) RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->stage_rays[k]), kChunkRays * sizeof(rtp_ray)));
+            if (!ds->stage_hits[k]) RTP_CUDA(cudaMalloc(&ds->stage_hits[k], kChunkRays * sizeof(rtp_hit_full)));
         }
-        int rc = launch_trace(ds, ds->stage_rays[k], m, ds->stage_hits[k], full ? OUT_FULL : OUT_HIT, false, count ? ds->counters : nullptr, st);
-        if (rc != RTP_OK) return rc;
-        ++launches;
-        RTP_CUDA(cudaMemcpyAsync(static_cast<char*>(hits_out) + off * hit_bytes, ds->stage_hits[k], m * hit_bytes, cudaMemcpyDeviceToHost, st));
+        if (count) RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), ds->streams[0]));
+        RTP_CUDA(cudaEventRecord(ds->ev_begin, ds->streams[0]));
+        for (int k = 1; k < kPipeDepth; ++k) RTP_CUDA(cudaStreamWaitEvent(ds->streams[k], ds->ev_begin, 0));
     }
-    cudaEvent_t done[kPipeDepth];
-    for (int k = 1; k < kPipeDepth; ++k) {
-        RTP_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
-        RTP_CUDA(cudaEventRecord(done[k], ds->streams[k]));
-        RTP_CUDA(cudaStreamWaitEvent(ds->streams[0], done[k], 0));
+    size_t launches = 0, chunk_id = 0;
+    for (size_t off = 0; off < n && rc == RTP_OK; off += kChunkRays, ++chunk_id) {
+        const size_t m = std::min(kChunkRays, n - off);
+        DeviceScene* ds = devs[chunk_id % N];
+        const int k = static_cast<int>((chunk_id / N) % kPipeDepth);
+        cudaStream_t st = ds->streams[k];
+        cudaError_t e = N > 1 ? cudaSetDevice(ds->device) : cudaSuccess;
+        if (e == cudaSuccess) {
+            if (camera) {
+                camera_rays_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(*camera, width, height, ds->stage_rays[k], off, m);
+                e = cudaGetLastError();
+                ++launches;
+            } else {
+                e = cudaMemcpyAsync(ds->stage_rays[k], rays + off, m * sizeof(rtp_ray), cudaMemcpyHostToDevice, st);
+            }
+        }
+        if (e != cudaSuccess) { rc = set_error(RTP_ERR_CUDA, std::string("trace chunk: ") + cudaGetErrorString(e)); break; }
+        rc = launch_trace(ds, ds->stage_rays[k], m, ds->stage_hits[k], full ? OUT_FULL : OUT_HIT, false, count ? ds->counters : nullptr, st);
+        if (rc != RTP_OK) break;
+        launches += ds->last_trace_launches;
+        e = cudaMemcpyAsync(static_cast<char*>(hits_out) + off * hit_bytes, ds->stage_hits[k], m * hit_bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = set_error(RTP_ERR_CUDA, std::string("trace chunk: ") + cudaGetErrorString(e));
     }
-    RTP_CUDA(cudaEventRecord(ds->ev_end, ds->streams[0]));
-    RTP_CUDA(cudaEventSynchronize(ds->ev_end));
-    for (int k = 1; k < kPipeDepth; ++k) cudaEventDestroy(done[k]);
-    if (stats) {
-        Counters c;
-        RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
-        float ms = 0.f;
-        RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
-        std::memset(stats, 0, sizeof *stats);
-        stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
-        stats->device_ms = ms; stats->kernel_launches = launches;
+    // drain every device that was given work (also after an error: nothing may stay in flight on the staging buffers)
+    rtp_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (size_t d = 0; d < used; ++d) {
+        DeviceScene* ds = devs[d];
+        cudaSetDevice(ds->device);
+        cudaError_t e = cudaSuccess;
+        for (int k = 1; k < kPipeDepth && e == cudaSuccess; ++k) e = cudaStreamSynchronize(ds->streams[k]);
+        if (e == cudaSuccess) e = cudaEventRecord(ds->ev_end, ds->streams[0]);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ds->streams[0]);
+        else cudaStreamSynchronize(ds->streams[0]);
+        if (e != cudaSuccess && rc == RTP_OK) rc = set_error(RTP_ERR_CUDA, std::string("trace: ") + cudaGetErrorString(e));
+        if (stats && rc == RTP_OK) {
+            Counters c;
+            float ms = 0.f;
+            e = cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end);
+            if (e != cudaSuccess) { rc = set_error(RTP_ERR_CUDA, std::string("trace stats: ") + cudaGetErrorString(e)); continue; }
+            total.rays += c.rays; total.node_visits += c.node_visits; total.triangle_tests += c.triangle_tests; total.sphere_tests += c.sphere_tests;
+            total.leaf_gates += c.leaf_gates; total.conservative_violations += c.violations; total.order_rewalks += c.rewalks;
+            total.device_ms = std::max(total.device_ms, static_cast<double>(ms));
+        }
     }
-    return RTP_OK;
+    if (N > 1) cudaSetDevice(scene->dev->device);
+    if (stats && rc == RTP_OK) { total.kernel_launches = launches; *stats = total; }
+    return rc;
 }
 
 template <int MAXB>
@@ -2321,20 +2376,46 @@ static int wave_reserve(DeviceScene* ds, size_t capacity, uint32_t bounces) {
 
 constexpr unsigned int kSrgbFixCap = 1u << 16;
 
-// d_rgba8 != nullptr: the output stage runs on the device (srgb8_kernel) instead of write_frame_kernel
-static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* p, double* d_rgb, double* d_fg, rtp_stats* stats,
-                         cudaStream_t st, uchar4* d_rgba8 = nullptr) {
-    DeviceScene* ds = scene->dev;
+// d_rgba8 != nullptr: the output stage runs on the device (srgb8_kernel) instead of write_frame_kernel.
+// Two phases so that one host thread can keep several devices busy: render_enqueue queues every launch of the frame on `st`
+// without synchronising, render_finish waits for them and reads the counters back.
+static cudaEvent_t next_mark(DeviceScene* ds, cudaStream_t st) {
+    if (ds->ev_used == ds->ev_pool.size()) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+        ds->ev_pool.push_back(ev);
+    }
+    cudaEvent_t ev = ds->ev_pool[ds->ev_used++];
+    cudaEventRecord(ev, st);
+    return ev;
+}
+
+static int render_enqueue(DeviceScene* ds, const rtp_camera* camera, const rtp_render_params* p, double* d_rgb, double* d_fg, bool want_stats,
+                          cudaStream_t st, uchar4* d_rgba8 = nullptr) {
     if (p->max_bounce < 1) return set_error(RTP_ERR_INVALID, "assert!(depth >= 1) (render.rs:97)");
     if (p->max_bounce > 128) return set_error(RTP_ERR_UNSUPPORTED, "max_bounce > 128");
     if (p->width == 0 || p->height == 0 || p->sample_end < p->sample_begin || p->num_samples == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
     if (static_cast<uint64_t>(p->width) * p->height > 0xFFFFFFFFull) return set_error(RTP_ERR_INVALID, "frame too large");
     const uint32_t tx = p->tile_x, ty = p->tile_y;
     if (tx >= p->width || ty >= p->height) return set_error(RTP_ERR_INVALID, "tile outside frame");
-    const uint32_t tw = p->tile_w ? p->tile_w : p->width - tx, th = p->tile_h ? p->tile_h : p->height - ty;
-    if (static_cast<uint64_t>(tx) + tw > p->width || static_cast<uint64_t>(ty) + th > p->height) return set_error(RTP_ERR_INVALID, "tile outside frame");
+    const uint32_t tw = p->tile_w ? p->tile_w : p->width - tx, th_full = p->tile_h ? p->tile_h : p->height - ty;
+    if (static_cast<uint64_t>(tx) + tw > p->width || static_cast<uint64_t>(ty) + th_full > p->height) return set_error(RTP_ERR_INVALID, "tile outside frame");
+    const uint32_t rs = p->row_stride ? p->row_stride : 1u, ro = p->row_offset;
+    if (ro >= rs) return set_error(RTP_ERR_INVALID, "row_offset must be below row_stride");
+    const uint32_t th = ro < th_full ? (th_full - ro + rs - 1u) / rs : 0u;  // rows of the tile rectangle this call renders
 
+    // the scratch below is shared by every render on this scene: a render queued on another stream must be over first
+    if (ds->render_pending) RTP_CUDA(cudaStreamWaitEvent(st, ds->render_done, 0));
+    ds->ev_used = 0;
+    ds->pending_launches = 0;
+    ds->pending_paths = 0;
     const size_t npix = static_cast<size_t>(tw) * th;
+    if (want_stats) {
+        RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), st));
+        RTP_CUDA(cudaEventRecord(ds->ev_begin, st));
+        RTP_CUDA(cudaEventRecord(ds->ev_end, st));
+    }
+    if (npix == 0) return RTP_OK;  // no row of the rectangle falls to this call
     const uint32_t ns_total = p->sample_end - p->sample_begin;
     // samples per launch: up to 32 Mi paths (wavefront queues 176 B + 48 B x max_bounce per path, scratch 32 B), within the memory
     // budget fixed when the scene was uploaded (a sixth of the free HBM, at most 24 GiB). Big launches matter: every launch pays
@@ -2365,10 +2446,10 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
     DRender rp;
     rp.width = p->width; rp.height = p->height; rp.max_bounce = p->max_bounce;
     rp.tile_x = tx; rp.tile_y = ty; rp.tile_w = tw; rp.tile_h = th;
+    rp.row_offset = ro; rp.row_stride = rs;
     rp._pad = 0; rp.seed = p->seed;
 
-    RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), st));
-    if (stats) RTP_CUDA(cudaEventRecord(ds->ev_begin, st));
+    if (!want_stats) RTP_CUDA(cudaMemsetAsync(ds->counters, 0, sizeof(Counters), st));
     size_t launches = 0;
     bool first = true;
     if (ns_total == 0) RTP_CUDA(cudaMemsetAsync(ds->acc, 0, npix * sizeof(double4), st));
@@ -2393,20 +2474,22 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
                 // a late bounce costs the latency of ONE ray segment (~30 us of dependent instructions, tools/small_batches.py),
                 // not a launch.
                 const bool tail_certain = total <= ds->tail_threshold;
+                if (want_stats) next_mark(ds, st);  // even marks open a traversal span, odd marks close it
                 if (ds->tail_threshold && (tail_certain || (ds->tail_offer && b > 0))) {
                     TailArgs ta{ds->wave, rp, ds->scratch, b, ds->tail_threshold};
                     rc = launch_trace(ds, ds->wave.rays[b & 1], total, nullptr, OUT_TAIL, count, ds->counters, st, ds->wave.count + b, &ta);
                     if (rc != RTP_OK) return rc;
                     ++launches;
-                    if (tail_certain) break;
+                    if (tail_certain) { if (want_stats) next_mark(ds, st); break; }
                 }
                 rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, ds->wave.count + b);
                 if (rc != RTP_OK) return rc;
-                if ((rc = debug_sync(ds, st, "trace_persistent_kernel<OUT_WAVE>", b)) != RTP_OK) return rc;
+                if (want_stats) next_mark(ds, st);
+                if ((rc = debug_sync(ds, st, "trace kernel <OUT_WAVE>", b)) != RTP_OK) return rc;
                 wave_shade_kernel<<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch);
                 RTP_CUDA(cudaGetLastError());
                 if ((rc = debug_sync(ds, st, "wave_shade_kernel", b)) != RTP_OK) return rc;
-                launches += 2;
+                launches += ds->last_trace_launches + 1;
             }
         } else {
             if (p->max_bounce <= 8) launch_render_paths<8>(ds, cam, rp, total, count, st);
@@ -2430,19 +2513,40 @@ static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_r
     }
     RTP_CUDA(cudaGetLastError());
     ++launches;
-    if (stats) {
-        RTP_CUDA(cudaEventRecord(ds->ev_end, st));
-        RTP_CUDA(cudaEventSynchronize(ds->ev_end));
-        Counters c;
-        RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
-        float ms = 0.f;
-        RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
-        std::memset(stats, 0, sizeof *stats);
-        stats->rays = c.rays; stats->paths = static_cast<uint64_t>(npix) * ns_total;
-        stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
-        stats->device_ms = ms; stats->kernel_launches = launches;
-    }
+    ds->pending_launches = launches;
+    ds->pending_paths = static_cast<uint64_t>(npix) * ns_total;
+    if (want_stats) RTP_CUDA(cudaEventRecord(ds->ev_end, st));
+    RTP_CUDA(cudaEventRecord(ds->render_done, st));
+    ds->render_pending = true;
     return RTP_OK;
+}
+
+// waits for the frame enqueued last on this device and fills `stats` (all fields)
+static int render_finish(DeviceScene* ds, rtp_stats* stats) {
+    RTP_CUDA(cudaEventSynchronize(ds->ev_end));
+    Counters c;
+    RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
+    double trace_ms = 0.0;
+    for (size_t k = 0; k + 1 < ds->ev_used; k += 2) {
+        float span = 0.f;
+        if (cudaEventElapsedTime(&span, ds->ev_pool[k], ds->ev_pool[k + 1]) == cudaSuccess) trace_ms += span;
+    }
+    std::memset(stats, 0, sizeof *stats);
+    stats->rays = c.rays; stats->paths = ds->pending_paths;
+    stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
+    stats->device_ms = ms; stats->kernel_launches = ds->pending_launches;
+    stats->trace_ms = trace_ms; stats->shade_ms = std::max(0.0, static_cast<double>(ms) - trace_ms);
+    return RTP_OK;
+}
+
+static int render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* p, double* d_rgb, double* d_fg, rtp_stats* stats,
+                         cudaStream_t st, uchar4* d_rgba8 = nullptr) {
+    DeviceScene* ds = scene->dev;
+    int rc = render_enqueue(ds, camera, p, d_rgb, d_fg, stats != nullptr, st, d_rgba8);
+    if (rc != RTP_OK) return rc;
+    return stats ? render_finish(ds, stats) : RTP_OK;
 }
 
 }  // namespace rtp
@@ -2522,14 +2626,38 @@ void rtp_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
+// device_mask == 0: the device bound by rtp_init (or device 0)
+static int scene_create_impl(const rtp_scene_desc* desc, uint32_t device_mask, rtp_scene** out) {
     if (!out) return set_error(RTP_ERR_INVALID, "null argument");
     *out = nullptr;
     try {
         rtp_scene* s = new rtp_scene();
-        int rc = flatten_scene(desc, &s->flat, /*device_build=*/true);  // validates before it touches the device
-        if (rc == RTP_OK) rc = device_scene_upload(s->flat, &s->dev);
-        if (rc != RTP_OK) { delete s; return rc; }
+        auto bail = [&](int code) { for (DeviceScene* ds : s->devs) { cudaSetDevice(ds->device); device_scene_free(ds); } delete s; return code; };
+        int rc = RTP_OK;
+        if (device_mask) {
+            for (int d = 0; d < 32 && rc == RTP_OK; ++d)
+                if ((device_mask >> d) & 1u) rc = check_device(d);
+            if (rc != RTP_OK) return bail(rc);
+            int first = 0;
+            while (!((device_mask >> first) & 1u)) ++first;
+            if (g_device < 0) g_device = first;
+            cudaSetDevice(first);  // the device part of the build (reference leaf order of big scenes) runs on the first device
+        }
+        rc = flatten_scene(desc, &s->flat, /*device_build=*/true);  // validates before it touches the device
+        if (rc != RTP_OK) return bail(rc);
+        if (!device_mask) {
+            if ((rc = require_device()) != RTP_OK) return bail(rc);
+            device_mask = 1u << g_device;
+        }
+        for (int d = 0; d < 32 && rc == RTP_OK; ++d)
+            if ((device_mask >> d) & 1u) {
+                DeviceScene* ds = nullptr;
+                rc = device_scene_upload(s->flat, d, &ds);
+                if (rc == RTP_OK) s->devs.push_back(ds);
+            }
+        if (rc != RTP_OK) return bail(rc);
+        s->dev = s->devs[0];
+        cudaSetDevice(s->dev->device);
         s->n_leaves = static_cast<uint32_t>(s->flat.prims.size());
         s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? s->flat.n_reference_nodes : 0u;
         // the host copies of the big arrays are no longer needed
@@ -2548,9 +2676,26 @@ int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) {
     }
 }
 
+int rtp_scene_create_multi(const rtp_scene_desc* desc, uint32_t device_mask, rtp_scene** out) {
+    if (device_mask == 0) { if (out) *out = nullptr; return set_error(RTP_ERR_INVALID, "empty device mask"); }
+    return scene_create_impl(desc, device_mask, out);
+}
+
+int rtp_scene_create(const rtp_scene_desc* desc, rtp_scene** out) { return scene_create_impl(desc, 0u, out); }
+
+int rtp_scene_devices(const rtp_scene* scene, uint32_t* device_mask_out) {
+    if (!scene || !device_mask_out) return set_error(RTP_ERR_INVALID, "null argument");
+    uint32_t m = 0;
+    for (const DeviceScene* ds : scene->devs) m |= 1u << ds->device;
+    *device_mask_out = m;
+    return RTP_OK;
+}
+
 void rtp_scene_destroy(rtp_scene* scene) {
     if (!scene) return;
-    device_scene_free(scene->dev);
+    const int primary = scene->dev ? scene->dev->device : -1;
+    for (DeviceScene* ds : scene->devs) { cudaSetDevice(ds->device); device_scene_free(ds); }
+    if (primary >= 0) cudaSetDevice(primary);
     delete scene;
 }
 
@@ -2682,74 +2827,112 @@ int rtp_render_device(rtp_scene* scene, const rtp_camera* camera, const rtp_rend
     return render_device(scene, camera, params, d_rgb_out, d_foreground_out, stats, static_cast<cudaStream_t>(cuda_stream));
 }
 
+// rtp_render / rtp_render_srgb8: host buffers, one or several devices. The rows of the tile rectangle are dealt out round-robin to
+// the devices taking part (params->device_mask), every device renders ALL samples of its rows and copies them straight into the
+// caller's frame: no exchange between devices, and since a pixel's value depends only on (seed, pixel, sample) the frame is
+// bit-identical to a one-device render. All devices are driven from this one host thread: render_enqueue never synchronises.
+static int render_host(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, double* rgb_out, double* foreground_out,
+                       uint8_t* rgba_out, rtp_stats* stats) {
+    const size_t npx = static_cast<size_t>(params->width) * params->height;
+    if (npx == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
+    std::vector<DeviceScene*> devs;
+    for (DeviceScene* ds : scene->devs)
+        if (params->device_mask == 0 || ((params->device_mask >> ds->device) & 1u)) devs.push_back(ds);
+    if (devs.empty()) return set_error(RTP_ERR_INVALID, "device_mask names no device of this scene");
+    const uint32_t N = static_cast<uint32_t>(devs.size());
+    const uint32_t rs0 = params->row_stride ? params->row_stride : 1u, ro0 = params->row_offset;
+    const uint32_t W = params->width, tx = params->tile_x, ty = params->tile_y;
+    const uint32_t tw = params->tile_w ? params->tile_w : W - tx, th_full = params->tile_h ? params->tile_h : params->height - ty;
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (DeviceScene* ds : devs) locks.emplace_back(ds->lock);
+    int rc = RTP_OK;
+    for (uint32_t k = 0; k < N && rc == RTP_OK; ++k) {
+        DeviceScene* ds = devs[k];
+        RTP_CUDA(cudaSetDevice(ds->device));
+        cudaStream_t st = ds->streams[0];
+        rtp_render_params p = *params;
+        p.row_offset = ro0 + k * rs0;  // rows ro0 + m * rs0 of the caller's split; device k takes m = k, k + N, ...
+        p.row_stride = rs0 * N;
+        if (rgba_out) {
+            if (ds->frame8_elems < npx) {
+                cudaFree(ds->frame8); ds->frame8 = nullptr; ds->frame8_elems = 0;
+                RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->frame8), npx * sizeof(uchar4)));
+                ds->frame8_elems = npx;
+            }
+            if (!ds->fixes) {
+                RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->fixes), kSrgbFixCap * sizeof(SrgbFix)));
+                RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->n_fixes), sizeof(unsigned int)));
+            }
+        } else if (ds->frame_elems < npx * 4) {
+            cudaFree(ds->frame); ds->frame = nullptr; ds->frame_elems = 0;
+            RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->frame), npx * 4 * sizeof(double)));
+            ds->frame_elems = npx * 4;
+        }
+        rc = render_enqueue(ds, camera, &p, rgba_out ? nullptr : ds->frame, (!rgba_out && foreground_out) ? ds->frame + npx * 3 : nullptr, stats != nullptr, st,
+                            rgba_out ? ds->frame8 : nullptr);
+        if (rc != RTP_OK) break;
+        // only the rows this device rendered travel back (main.rs:86-87 writes per tile)
+        if (p.row_offset >= th_full || tx >= W) continue;
+        const uint32_t rows = (th_full - p.row_offset + p.row_stride - 1u) / p.row_stride;
+        const size_t first = static_cast<size_t>(tx) + static_cast<size_t>(ty + p.row_offset) * W;
+        const size_t row_px = static_cast<size_t>(W) * p.row_stride;
+        if (rgba_out) {
+            RTP_CUDA(cudaMemcpy2DAsync(rgba_out + 4 * first, row_px * 4, ds->frame8 + first, row_px * 4, static_cast<size_t>(tw) * 4, rows, cudaMemcpyDeviceToHost, st));
+            RTP_CUDA(cudaMemcpyAsync(&ds->n_fix_host, ds->n_fixes, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        } else {
+            RTP_CUDA(cudaMemcpy2DAsync(rgb_out + 3 * first, row_px * 24, ds->frame + 3 * first, row_px * 24, static_cast<size_t>(tw) * 24, rows, cudaMemcpyDeviceToHost, st));
+            if (foreground_out)
+                RTP_CUDA(cudaMemcpy2DAsync(foreground_out + first, row_px * 8, ds->frame + npx * 3 + first, row_px * 8, static_cast<size_t>(tw) * 8, rows, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    // wait for every device that was given work, even after an error on a later one
+    rtp_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (uint32_t k = 0; k < N; ++k) {
+        DeviceScene* ds = devs[k];
+        cudaSetDevice(ds->device);
+        cudaError_t e = cudaStreamSynchronize(ds->streams[0]);
+        if (e != cudaSuccess && rc == RTP_OK) rc = set_error(RTP_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+        if (rc != RTP_OK) continue;
+        if (rgba_out && ds->pending_launches) {
+            const unsigned int n_fix = ds->n_fix_host;
+            if (n_fix > kSrgbFixCap) { rc = set_error(RTP_ERR_UNSUPPORTED, "more than 65536 pixels need the host libm fix-up; use rtp_render + rtp_frame_to_srgb8"); continue; }
+            if (n_fix) {  // redo the borderline pixels with the host libm (utility.rs:213 powf as the reference's target evaluates it)
+                std::vector<SrgbFix> fixes(n_fix);
+                if (cudaMemcpy(fixes.data(), ds->fixes, n_fix * sizeof(SrgbFix), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = set_error(RTP_ERR_CUDA, "fix-up list copy"); continue; }
+                for (const SrgbFix& f : fixes) {
+                    uint8_t px[4];
+                    rtp_frame_to_srgb8(f.rgb, 1, 1, px);
+                    std::memcpy(rgba_out + 4 * static_cast<size_t>(f.pixel), px, 3);
+                }
+            }
+        }
+        if (stats) {
+            rtp_stats one;
+            int r2 = render_finish(ds, &one);
+            if (r2 != RTP_OK) { rc = r2; continue; }
+            total.rays += one.rays; total.paths += one.paths; total.node_visits += one.node_visits; total.triangle_tests += one.triangle_tests;
+            total.sphere_tests += one.sphere_tests; total.leaf_gates += one.leaf_gates; total.conservative_violations += one.conservative_violations;
+            total.order_rewalks += one.order_rewalks; total.kernel_launches += one.kernel_launches;
+            total.device_ms = std::max(total.device_ms, one.device_ms);  // the devices run side by side
+            total.trace_ms = std::max(total.trace_ms, one.trace_ms); total.shade_ms = std::max(total.shade_ms, one.shade_ms);
+        }
+    }
+    cudaSetDevice(scene->dev->device);
+    if (stats && rc == RTP_OK) *stats = total;
+    return rc;
+}
+
 int rtp_render_srgb8(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, uint8_t* rgba_out, rtp_stats* stats) {
     if (!scene || !camera || !params || !rgba_out) return set_error(RTP_ERR_INVALID, "null argument");
     if (params->flags & RTP_RENDER_RAW_SUMS) return set_error(RTP_ERR_INVALID, "RTP_RENDER_RAW_SUMS has no 8-bit output");
-    DeviceScene* ds = scene->dev;
-    std::lock_guard<std::mutex> guard(ds->lock);
-    RTP_CUDA(cudaSetDevice(ds->device));
-    const size_t npx = static_cast<size_t>(params->width) * params->height;
-    if (npx == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
-    if (ds->frame8_elems < npx) {
-        cudaFree(ds->frame8); ds->frame8 = nullptr; ds->frame8_elems = 0;
-        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->frame8), npx * sizeof(uchar4)));
-        ds->frame8_elems = npx;
-    }
-    if (!ds->fixes) {
-        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->fixes), kSrgbFixCap * sizeof(SrgbFix)));
-        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->n_fixes), sizeof(unsigned int)));
-    }
-    cudaStream_t st = ds->streams[0];
-    int rc = render_device(scene, camera, params, nullptr, nullptr, stats, st, ds->frame8);
-    if (rc != RTP_OK) return rc;
-    const uint32_t W = params->width, tx = params->tile_x, ty = params->tile_y;
-    const uint32_t tw = params->tile_w ? params->tile_w : W - tx, th = params->tile_h ? params->tile_h : params->height - ty;
-    const size_t first = static_cast<size_t>(tx) + static_cast<size_t>(ty) * W;
-    RTP_CUDA(cudaMemcpy2DAsync(rgba_out + 4 * first, static_cast<size_t>(W) * 4, ds->frame8 + first, static_cast<size_t>(W) * 4, static_cast<size_t>(tw) * 4, th,
-                               cudaMemcpyDeviceToHost, st));
-    unsigned int n_fix = 0;
-    RTP_CUDA(cudaMemcpyAsync(&n_fix, ds->n_fixes, sizeof n_fix, cudaMemcpyDeviceToHost, st));
-    RTP_CUDA(cudaStreamSynchronize(st));
-    if (n_fix > kSrgbFixCap) return set_error(RTP_ERR_UNSUPPORTED, "more than 65536 pixels need the host libm fix-up; use rtp_render + rtp_frame_to_srgb8");
-    if (n_fix) {  // redo the borderline pixels with the host libm (utility.rs:213 powf as the reference's target evaluates it)
-        std::vector<SrgbFix> fixes(n_fix);
-        RTP_CUDA(cudaMemcpy(fixes.data(), ds->fixes, n_fix * sizeof(SrgbFix), cudaMemcpyDeviceToHost));
-        for (const SrgbFix& f : fixes) {
-            uint8_t px[4];
-            rtp_frame_to_srgb8(f.rgb, 1, 1, px);
-            std::memcpy(rgba_out + 4 * static_cast<size_t>(f.pixel), px, 3);
-        }
-    }
-    return RTP_OK;
+    return render_host(scene, camera, params, nullptr, nullptr, rgba_out, stats);
 }
 
 int rtp_render(rtp_scene* scene, const rtp_camera* camera, const rtp_render_params* params, double* rgb_out, double* foreground_out,
                rtp_stats* stats) {
     if (!scene || !camera || !params || !rgb_out) return set_error(RTP_ERR_INVALID, "null argument");
-    DeviceScene* ds = scene->dev;
-    std::lock_guard<std::mutex> guard(ds->lock);
-    RTP_CUDA(cudaSetDevice(ds->device));
-    const size_t npx = static_cast<size_t>(params->width) * params->height;
-    if (npx == 0) return set_error(RTP_ERR_INVALID, "bad frame parameters");
-    if (ds->frame_elems < npx * 4) {
-        cudaFree(ds->frame); ds->frame = nullptr; ds->frame_elems = 0;
-        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ds->frame), npx * 4 * sizeof(double)));
-        ds->frame_elems = npx * 4;
-    }
-    cudaStream_t st = ds->streams[0];
-    int rc = render_device(scene, camera, params, ds->frame, foreground_out ? ds->frame + npx * 3 : nullptr, stats, st);
-    if (rc != RTP_OK) return rc;
-    // only the tile rectangle was written (main.rs:86-87 writes per tile): copy back exactly those rows
-    const uint32_t W = params->width, tx = params->tile_x, ty = params->tile_y;
-    const uint32_t tw = params->tile_w ? params->tile_w : W - tx, th = params->tile_h ? params->tile_h : params->height - ty;
-    const size_t first = static_cast<size_t>(tx) + static_cast<size_t>(ty) * W;
-    RTP_CUDA(cudaMemcpy2DAsync(rgb_out + 3 * first, static_cast<size_t>(W) * 24, ds->frame + 3 * first, static_cast<size_t>(W) * 24,
-                               static_cast<size_t>(tw) * 24, th, cudaMemcpyDeviceToHost, st));
-    if (foreground_out)
-        RTP_CUDA(cudaMemcpy2DAsync(foreground_out + first, static_cast<size_t>(W) * 8, ds->frame + npx * 3 + first, static_cast<size_t>(W) * 8,
-                                   static_cast<size_t>(tw) * 8, th, cudaMemcpyDeviceToHost, st));
-    RTP_CUDA(cudaStreamSynchronize(st));
-    return RTP_OK;
+    return render_host(scene, camera, params, rgb_out, foreground_out, nullptr, stats);
 }
 
 }  // extern "C"

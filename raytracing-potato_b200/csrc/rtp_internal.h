@@ -168,7 +168,7 @@ int flatten_scene(const rtp_scene_desc* desc, FlatScene* out, bool device_build 
 struct DeviceScene;
 int ensure_device();  // binds device 0 if rtp_init has not been called; RTP_ERR_CUDA without a usable sm_100 GPU
 int device_reference_order(const double* boxes /* n x {min xyz, max xyz} */, uint32_t n, uint32_t* order_out /* item index by DFS rank */);
-int device_scene_upload(const FlatScene& flat, DeviceScene** out);
+int device_scene_upload(const FlatScene& flat, int device /* < 0: the bound device */, DeviceScene** out);
 void device_scene_free(DeviceScene* ds);
 uint64_t device_scene_bytes(const DeviceScene* ds);
 
@@ -176,6 +176,7 @@ uint64_t device_scene_bytes(const DeviceScene* ds);
 
 struct rtp_scene {
     rtp::FlatScene flat;  // nodes/prims/attrs are released after upload; leaf_order is kept
-    rtp::DeviceScene* dev = nullptr;
+    rtp::DeviceScene* dev = nullptr;          // devs[0]: the device the *_device entry points use
+    std::vector<rtp::DeviceScene*> devs;      // one replica per device of rtp_scene_create_multi's mask
     uint32_t n_leaves = 0, n_nodes = 0;
 };
