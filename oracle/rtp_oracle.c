@@ -205,11 +205,19 @@ typedef struct {
     rtp_texture t;
 } orc_texture;
 
+typedef struct {
+    orc_node* nodes;
+    uint32_t n_nodes, root, depth;
+} orc_tree; /* bvh.rs:27-34 Bvh of a NESTED Hittable::Bvh (its leaves are a run of orc_scene.nested) */
+
 struct orc_scene {
     uint32_t root_kind;
     uint32_t n_meshes, n_hittables, n_materials, n_textures;
     rtp_mesh* meshes; /* deep copies */
     rtp_hittable* hittables;
+    rtp_hittable* nested;   /* items of nested List / Bvh hittables (rtp_scene_desc.nested) */
+    uint32_t n_nested;
+    orc_tree* nested_tree;  /* [n_nested]: the tree of the nested Bvh whose run starts at that index, nodes == NULL elsewhere */
     rtp_material* materials;
     orc_texture* textures;
     rtp_emit background;
@@ -225,10 +233,25 @@ typedef struct {
     double t;
     v3 position, normal;
     double u, v;
+    uint32_t material; /* the MaterialId half of Option<(Hit, MaterialId)> (hittable.rs:19) */
 } orc_hit;
 
-/* hittable.rs:124-140 bounding boxes */
-static void hittable_bbox(const orc_scene* s, const rtp_hittable* h, double bmin[3], double bmax[3]) {
+/* hittable.rs:27-34, 124-147 bounding boxes. Returns 0, or 1 where the reference panics: the box of a Bvh (hittable.rs:32) */
+static int hittable_bbox(const orc_scene* s, const rtp_hittable* h, double bmin[3], double bmax[3]) {
+    if (h->kind == RTP_HITTABLE_BVH) return 1;
+    if (h->kind == RTP_HITTABLE_LIST) { /* hittable.rs:142-147 bounding_box_list: AABB::default() when empty, else a left fold of unions */
+        const rtp_hittable* items = s->nested + h->mesh;
+        for (int k = 0; k < 3; ++k) bmin[k] = bmax[k] = 0.0;
+        for (uint32_t i = 0; i < h->triangle; ++i) {
+            double lo[3], hi[3];
+            if (hittable_bbox(s, &items[i], lo, hi)) return 1;
+            for (int k = 0; k < 3; ++k) { /* utility.rs:130-135 AABB::union */
+                bmin[k] = i ? f64_min(bmin[k], lo[k]) : lo[k];
+                bmax[k] = i ? f64_max(bmax[k], hi[k]) : hi[k];
+            }
+        }
+        return 0;
+    }
     if (h->kind == RTP_HITTABLE_SPHERE) {
         for (int k = 0; k < 3; ++k) {
             bmin[k] = h->center[k] - h->radius;
@@ -244,6 +267,7 @@ static void hittable_bbox(const orc_scene* s, const rtp_hittable* h, double bmin
             bmax[k] = f64_max(f64_max(a[k], b[k]), c[k]);
         }
     }
+    return 0;
 }
 
 /* bvh.rs:60-64: order by 0.5*(min+max) on the axis. The reference uses sort_unstable_by, whose
@@ -287,6 +311,33 @@ static uint32_t make_bvh(orc_scene* s, orc_item* items, size_t n, int axis, uint
     return s->n_nodes++;
 }
 
+/* bvh.rs:70-91 Bvh::new over `n` hittables: boxes, then make_bvh. strict: NaN centroids and Bvh items are errors (the reference panics) */
+static int build_tree(orc_scene* s, const rtp_hittable* leaves, uint32_t n, int strict, orc_tree* out) {
+    orc_item* items = (orc_item*)malloc(sizeof(orc_item) * (n ? n : 1));
+    for (uint32_t i = 0; i < n; ++i) {
+        items[i].id = i;
+        if (hittable_bbox(s, &leaves[i], items[i].bmin, items[i].bmax)) {
+            free(items);
+            return fail(RTP_ERR_INVALID, "bounding box of a Bvh: \"Do not take the bounding box of a Bvh\" (hittable.rs:32)");
+        }
+        for (int k = 0; k < 3; ++k) {
+            double key = 0.5 * (items[i].bmin[k] + items[i].bmax[k]);
+            if (key != key && strict) { /* partial_cmp().unwrap() panics, bvh.rs:63 */
+                free(items);
+                return fail(RTP_ERR_INVALID, "NaN bounding-box centroid");
+            }
+        }
+    }
+    orc_node* keep_nodes = s->nodes; uint32_t keep_n = s->n_nodes, keep_depth = s->depth;
+    s->nodes = (orc_node*)calloc((size_t)2 * (n ? n : 1), sizeof(orc_node));
+    s->n_nodes = 0; s->depth = 0;
+    out->root = make_bvh(s, items, n, 0, 1);
+    out->nodes = s->nodes; out->n_nodes = s->n_nodes; out->depth = s->depth;
+    s->nodes = keep_nodes; s->n_nodes = keep_n; s->depth = keep_depth;
+    free(items);
+    return RTP_OK;
+}
+
 void orc_scene_destroy(orc_scene* s) {
     if (!s) return;
     if (s->meshes) {
@@ -296,6 +347,8 @@ void orc_scene_destroy(orc_scene* s) {
         }
     }
     if (s->textures) for (uint32_t i = 0; i < s->n_textures; ++i) free(s->textures[i].rgba);
+    if (s->nested_tree) for (uint32_t i = 0; i < s->n_nested; ++i) free(s->nested_tree[i].nodes);
+    free(s->nested_tree); free(s->nested);
     free(s->meshes); free(s->hittables); free(s->materials); free(s->textures); free(s->nodes);
     free(s);
 }
@@ -360,32 +413,49 @@ int orc_scene_create(const rtp_scene_desc* d, orc_scene** out) {
     }
     if (!check_emit(&d->background, d->n_textures)) { orc_scene_destroy(s); return fail(RTP_ERR_INVALID, "bad background"); }
     memcpy(s->hittables, d->hittables, sizeof(rtp_hittable) * d->n_hittables);
-    for (uint32_t i = 0; i < d->n_hittables; ++i) {
-        const rtp_hittable* h = &d->hittables[i];
-        int ok = 1;
-        if (h->kind == RTP_HITTABLE_SPHERE) ok = h->material < d->n_materials;
-        else if (h->kind == RTP_HITTABLE_TRIANGLE)
-            ok = h->mesh < d->n_meshes && (uint64_t)h->triangle + 3 <= d->meshes[h->mesh].n_indices;
-        else ok = 0;
-        if (!ok) { orc_scene_destroy(s); return fail(RTP_ERR_INVALID, "bad hittable"); }
-    }
-    /* bvh.rs:70-91 Bvh::new (also built for List roots so the differential test has leaf boxes) */
-    if (d->n_hittables) {
-        orc_item* items = (orc_item*)malloc(sizeof(orc_item) * d->n_hittables);
-        for (uint32_t i = 0; i < d->n_hittables; ++i) {
-            items[i].id = i;
-            hittable_bbox(s, &s->hittables[i], items[i].bmin, items[i].bmax);
-            for (int k = 0; k < 3; ++k) {
-                double key = 0.5 * (items[i].bmin[k] + items[i].bmax[k]);
-                if (key != key && d->root_kind == RTP_ROOT_BVH) { /* partial_cmp().unwrap() panics, bvh.rs:63 */
-                    free(items); orc_scene_destroy(s);
-                    return fail(RTP_ERR_INVALID, "NaN bounding-box centroid");
-                }
-            }
+    if (d->n_nested && !d->nested) { orc_scene_destroy(s); return fail(RTP_ERR_INVALID, "null nested table"); }
+    s->n_nested = d->n_nested;
+    s->nested = (rtp_hittable*)calloc(d->n_nested ? d->n_nested : 1, sizeof(rtp_hittable));
+    s->nested_tree = (orc_tree*)calloc(d->n_nested ? d->n_nested : 1, sizeof(orc_tree));
+    if (d->n_nested) memcpy(s->nested, d->nested, sizeof(rtp_hittable) * d->n_nested);
+    for (uint32_t pass = 0; pass < 2; ++pass) {
+        const rtp_hittable* tab = pass ? s->nested : s->hittables;
+        uint32_t n = pass ? s->n_nested : s->n_hittables;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtp_hittable* h = &tab[i];
+            int ok = 1;
+            if (h->kind == RTP_HITTABLE_SPHERE) ok = h->material < d->n_materials;
+            else if (h->kind == RTP_HITTABLE_TRIANGLE)
+                ok = h->mesh < d->n_meshes && (uint64_t)h->triangle + 3 <= d->meshes[h->mesh].n_indices;
+            else if (h->kind == RTP_HITTABLE_LIST || h->kind == RTP_HITTABLE_BVH)
+                /* a run of `nested`; a nested container's run lies entirely before the container itself, so nesting cannot cycle */
+                ok = (uint64_t)h->mesh + h->triangle <= (pass ? i : s->n_nested);
+            else ok = 0;
+            if (!ok) { orc_scene_destroy(s); return fail(RTP_ERR_INVALID, "bad hittable"); }
+            if (h->kind == RTP_HITTABLE_BVH && h->triangle == 0) { orc_scene_destroy(s); return fail(RTP_ERR_INVALID, "Bvh::new on an empty list is unreachable!() in the reference (bvh.rs:40)"); }
         }
-        s->nodes = (orc_node*)calloc((size_t)2 * d->n_hittables, sizeof(orc_node));
-        s->root = make_bvh(s, items, d->n_hittables, 0, 1);
-        free(items);
+    }
+    /* nested Bvh::new (bvh.rs:70-91), inner ones first (their runs come first) */
+    for (uint32_t pass = 0; pass < 2; ++pass) {
+        const rtp_hittable* tab = pass ? s->hittables : s->nested;
+        uint32_t n = pass ? s->n_hittables : s->n_nested;
+        for (uint32_t i = 0; i < n; ++i) {
+            const rtp_hittable* h = &tab[i];
+            if (h->kind != RTP_HITTABLE_BVH || s->nested_tree[h->mesh].nodes) continue;
+            int rc = build_tree(s, s->nested + h->mesh, h->triangle, 1, &s->nested_tree[h->mesh]);
+            if (rc) { orc_scene_destroy(s); return rc; }
+        }
+    }
+    /* bvh.rs:70-91 Bvh::new (also built for List roots of primitives so the differential test has leaf boxes) */
+    if (d->n_hittables) {
+        int any_bvh = 0;
+        for (uint32_t i = 0; i < d->n_hittables; ++i) { double lo[3], hi[3]; any_bvh |= hittable_bbox(s, &s->hittables[i], lo, hi); }
+        if (d->root_kind == RTP_ROOT_BVH || !any_bvh) {
+            orc_tree t;
+            int rc = build_tree(s, s->hittables, d->n_hittables, d->root_kind == RTP_ROOT_BVH, &t);
+            if (rc) { orc_scene_destroy(s); return rc; }
+            s->nodes = t.nodes; s->n_nodes = t.n_nodes; s->root = t.root; s->depth = t.depth;
+        }
     }
     *out = s;
     return RTP_OK;
@@ -410,7 +480,7 @@ static void leaf_order_rec(const orc_scene* s, uint32_t node, uint32_t* out, siz
 int orc_scene_leaf_order(const orc_scene* s, uint32_t* out, size_t cap) {
     if (!s || !out || cap < s->n_hittables) return fail(RTP_ERR_INVALID, "bad argument");
     size_t n = 0;
-    if (s->n_hittables) leaf_order_rec(s, s->root, out, &n);
+    if (s->n_hittables && s->nodes) leaf_order_rec(s, s->root, out, &n);
     return RTP_OK;
 }
 int orc_scene_node(const orc_scene* s, uint32_t node, double aabb[6], uint32_t lrl[3]) {
@@ -521,21 +591,51 @@ static inline uint32_t hittable_material(const orc_scene* s, const rtp_hittable*
     return h->kind == RTP_HITTABLE_SPHERE ? h->material : s->meshes[h->mesh].material;
 }
 
-/* hittable.rs:18-25 Hittable::hit for the primitive variants */
-static int hit_primitive(const orc_scene* s, uint32_t leaf, const orc_xray* r, orc_hit* hit, orc_counters* c) {
-    const rtp_hittable* h = &s->hittables[leaf];
-    if (h->kind == RTP_HITTABLE_SPHERE) { c->sphere_tests++; return hit_sphere(h, r, hit); }
-    c->triangle_tests++;
-    return hit_triangle(s, h, r, hit);
+static int hit_node(const orc_scene* s, const orc_node* nodes, const rtp_hittable* leaves, const orc_xray* ray, uint32_t node, orc_hit* hit, uint32_t* leaf, orc_counters* c);
+
+/* hittable.rs:18-25 Hittable::hit */
+static int hittable_hit(const orc_scene* s, const rtp_hittable* h, const orc_xray* r, orc_hit* hit, orc_counters* c) {
+    switch (h->kind) {
+    case RTP_HITTABLE_SPHERE:
+        c->sphere_tests++;
+        if (!hit_sphere(h, r, hit)) return 0;
+        hit->material = h->material;
+        return 1;
+    case RTP_HITTABLE_TRIANGLE:
+        c->triangle_tests++;
+        if (!hit_triangle(s, h, r, hit)) return 0;
+        hit->material = s->meshes[h->mesh].material; /* hittable.rs:107 */
+        return 1;
+    case RTP_HITTABLE_LIST: { /* hittable.rs:110-120 hit_list */
+        const rtp_hittable* items = s->nested + h->mesh;
+        int found = 0;
+        orc_xray ray = *r;
+        orc_hit nh;
+        for (uint32_t i = 0; i < h->triangle; ++i) {
+            if (hittable_hit(s, &items[i], &ray, &nh, c)) {
+                ray.t_max = nh.t;
+                *hit = nh; found = 1;
+            }
+        }
+        return found;
+    }
+    default: { /* RTP_HITTABLE_BVH: bvh.rs:121-124 Bvh::hit expands the ray again */
+        const orc_tree* t = &s->nested_tree[h->mesh];
+        orc_xray ray = *r;
+        ray.inv = v3_make(1.0 / ray.d.x, 1.0 / ray.d.y, 1.0 / ray.d.z);
+        uint32_t leaf;
+        return hit_node(s, t->nodes, s->nested + h->mesh, &ray, t->root, hit, &leaf, c);
+    }
+    }
 }
 
 /* bvh.rs:93-119 Bvh::hit_node */
-static int hit_node(const orc_scene* s, const orc_xray* ray, uint32_t node, orc_hit* hit, uint32_t* leaf, orc_counters* c) {
-    const orc_node* nd = &s->nodes[node];
+static int hit_node(const orc_scene* s, const orc_node* nodes, const rtp_hittable* leaves, const orc_xray* ray, uint32_t node, orc_hit* hit, uint32_t* leaf, orc_counters* c) {
+    const orc_node* nd = &nodes[node];
     c->node_visits++;
     if (nd->leaf != RTP_MISS) {
         if (aabb_collide(nd->bmin, nd->bmax, ray)) {
-            if (hit_primitive(s, nd->leaf, ray, hit, c)) { *leaf = nd->leaf; return 1; }
+            if (hittable_hit(s, &leaves[nd->leaf], ray, hit, c)) { *leaf = nd->leaf; return 1; }
         }
         return 0;
     }
@@ -544,23 +644,23 @@ static int hit_node(const orc_scene* s, const orc_xray* ray, uint32_t node, orc_
     orc_xray r = *ray; /* bvh.rs:105 clone */
     orc_hit h;
     uint32_t l;
-    if (hit_node(s, &r, nd->left, &h, &l, c)) {
+    if (hit_node(s, nodes, leaves, &r, nd->left, &h, &l, c)) {
         r.t_max = h.t; /* bvh.rs:107 */
         *hit = h; *leaf = l; found = 1;
     }
-    if (hit_node(s, &r, nd->right, &h, &l, c)) {
+    if (hit_node(s, nodes, leaves, &r, nd->right, &h, &l, c)) {
         *hit = h; *leaf = l; found = 1; /* bvh.rs:111 replace */
     }
     return found;
 }
 
-/* hittable.rs:110-120 hit_list over the primitive list */
+/* hittable.rs:110-120 hit_list over the root list */
 static int hit_list(const orc_scene* s, const orc_xray* ray, orc_hit* hit, uint32_t* leaf, orc_counters* c) {
     int found = 0;
     orc_xray r = *ray;
     orc_hit h;
     for (uint32_t i = 0; i < s->n_hittables; ++i) {
-        if (hit_primitive(s, i, &r, &h, c)) {
+        if (hittable_hit(s, &s->hittables[i], &r, &h, c)) {
             r.t_max = h.t;
             *hit = h; *leaf = i; found = 1;
         }
@@ -568,7 +668,7 @@ static int hit_list(const orc_scene* s, const orc_xray* ray, orc_hit* hit, uint3
     return found;
 }
 
-/* `scene.hit(ray, scene_data)` on the root (render.rs:105,133) */
+/* `scene.hit(ray, scene_data)` on the root (render.rs:105,133). *leaf = index of the winning item of the root container */
 static int scene_hit(const orc_scene* s, const rtp_ray* ray, int force_list, orc_hit* hit, uint32_t* leaf, orc_counters* c) {
     c->rays++;
     if (s->root_kind == RTP_ROOT_LIST || force_list) {
@@ -579,7 +679,7 @@ static int scene_hit(const orc_scene* s, const rtp_ray* ray, int force_list, orc
         return hit_list(s, &r, hit, leaf, c);
     }
     orc_xray r = expand(ray); /* bvh.rs:121-124 */
-    return hit_node(s, &r, s->root, hit, leaf, c);
+    return hit_node(s, s->nodes, s->hittables, &r, s->root, hit, leaf, c);
 }
 
 /* ------------------------------------------------------------------ textures ------------ */
@@ -758,7 +858,7 @@ static v3 trace_path_rec(const orc_scene* s, const rtp_ray* ray, uint32_t depth,
     v3 dir = v3_from(ray->direction);
     if (scene_hit(s, ray, 0, &hit, &leaf, c)) {
         if (first_hit) *first_hit = 1;
-        const rtp_material* m = &s->materials[hittable_material(s, &s->hittables[leaf])];
+        const rtp_material* m = &s->materials[hit.material];
         rtp_ray scattered;
         int has = scatter_evaluate(m, dir, &hit, rng, &scattered); /* material.rs:106 */
         v3 absorb = absorb_evaluate(s, m, &hit);                   /* material.rs:107 */
@@ -958,7 +1058,7 @@ static void* trace_worker(void* arg) {
         rtp_hit_full* o = &job->hits[k];
         if (s->n_hittables && scene_hit(s, &job->rays[k], job->mode == 1, &h, &leaf, &job->c)) {
             o->leaf = leaf;
-            o->material = hittable_material(s, &s->hittables[leaf]);
+            o->material = h.material;
             o->t = h.t;
             o->position[0] = h.position.x; o->position[1] = h.position.y; o->position[2] = h.position.z;
             o->normal[0] = h.normal.x; o->normal[1] = h.normal.y; o->normal[2] = h.normal.z;

@@ -480,10 +480,11 @@ def bvh_build_order(scene: ExampleScene):
     """`Bvh::new` on the host only (bvh.rs:70-91): (leaf ids in DFS order, SceneInfo). No device needed."""
     lib = A.load()
     desc, keep = build_desc(scene)
-    out = np.zeros(max(len(scene.hittables), 1), dtype=np.uint32)
     info = A.SceneInfo()
+    _check(lib, lib.rtp_bvh_build_order(C.byref(desc), None, 0, C.byref(info)))  # n_leaves: primitives after nested containers are flattened
+    out = np.zeros(max(info.n_leaves, 1), dtype=np.uint32)
     _check(lib, lib.rtp_bvh_build_order(C.byref(desc), A.ptr(out), len(out), C.byref(info)))
-    return out[: len(scene.hittables)], info
+    return out[: info.n_leaves], info
 
 
 class PinnedBuffer:

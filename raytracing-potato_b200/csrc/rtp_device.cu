@@ -233,9 +233,16 @@ __device__ __forceinline__ void closest_hit_bvh(const DSceneView& sc, D3 o, D3 d
 template <bool COUNT>
 __device__ __forceinline__ void closest_hit_list(const DSceneView& sc, D3 o, D3 d, double ray_tmin, HitRec& h, LocalCounters& lc) {
     h.slot = kNoPrim;
+    const D3 inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // only read for gated items (leaves of a nested Bvh, bvh.rs:121-124)
     for (uint32_t slot = 0; slot < sc.n_prims; ++slot) {
-        const uint32_t kind = __ldg(&sc.nodes[slot].kind);
+        const uint2 kp = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[slot].kind));  // kind, gate flag
+        const uint32_t kind = kp.x;
         const DPrim* p = sc.prims + slot;
+        if (kp.y) {  // bvh.rs:96: the leaf's own box first
+            const double* pb = p->bmin;
+            if (COUNT) lc.leaf_gates++;
+            if (!collide_literal(ldg2(pb), ldg2(pb + 2), ldg2(pb + 4), o, inv, ray_tmin, h.t)) continue;
+        }
         double t, u = 0.0, v = 0.0;
         bool hit;
         if (kind == RTP_HITTABLE_TRIANGLE) {
@@ -1426,7 +1433,15 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
         if (LIST) {
             // hittable.rs:110-120: every primitive, in caller order, no boxes
             if (w.next != kEnd) {
-                w.prim = w.next | (__ldg(&sc.nodes[w.next].kind) << 31); w.need_gate = false;
+                const uint2 kp = __ldg(reinterpret_cast<const uint2*>(&sc.nodes[w.next].kind));  // kind, gate flag
+                bool open = true;
+                if (kp.y) {  // a leaf of a nested Bvh (bvh.rs:96): its own box first, with the current t_max
+                    const double* pb = sc.prims[w.next].bmin;
+                    const double2 b0 = ldg2(pb), b1 = ldg2(pb + 2), b2 = ldg2(pb + 4);
+                    if (COUNT) lc.leaf_gates++;
+                    open = w.fast ? collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, w.h.t) : collide_literal(b0, b1, b2, w.o, w.inv, w.tmin, w.h.t);
+                }
+                if (open) { w.prim = w.next | (kp.x << 31); w.need_gate = false; }
                 w.next = w.next + 1 < sc.n_prims ? w.next + 1 : kEnd;
             }
         } else {
@@ -1921,7 +1936,7 @@ struct DeviceScene {
     int any_order = 0;                 // 1, 2: eligible rays take the any-order walk (RTP_TRAVERSAL), kernel variant ANY = 1 or 2
     uint32_t any_cap = 0;              // any-order stack entries per lane
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
-    Tuning tune{16, 6, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
+    Tuning tune{16, 4, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
     cudaStream_t streams[kPipeDepth] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t render_done = nullptr; // end of the last render enqueued: the next render (any stream) waits for it before it

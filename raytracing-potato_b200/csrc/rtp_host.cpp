@@ -484,6 +484,109 @@ static bool emit_ok(const rtp_emit& e, uint32_t n_textures) {
     return e.kind != RTP_EMIT_SKY_SPHERE || e.texture < n_textures;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Nested containers (hittable.rs:13-14: `List` and `Bvh` as items of another container). Everything the reference does with
+// them is again a SEQUENTIAL process over primitives: hit_list (hittable.rs:110-120) tests its items in order against the
+// shrinking ray and lets a later hit replace an earlier one; a Bvh leaf that holds a List is gated by the List's union box
+// (hittable.rs:142-147) and then runs that list; a Bvh inside a List is its own Bvh::hit, i.e. its leaves in its own
+// depth-first order, each behind its own box. So a scene with nesting flattens to one sequence of primitives, each with the
+// box that gates it (or none): exactly the form `Bvh::hit ≡ for leaf in order: if collide(gate) and hit(prim)` that
+// DESIGN.md §2 derives for the flat case. The reported leaf id is the index of the root container's item that holds the winner.
+// ---------------------------------------------------------------------------------------------
+struct SeqPrim {
+    const rtp_hittable* h;
+    uint32_t top;   // index of the root container's item this primitive belongs to
+    bool gated;
+    double gmin[3], gmax[3];
+};
+
+struct NestedFlattener {
+    const rtp_scene_desc* d;
+    std::vector<SeqPrim> seq;
+    int err = RTP_OK;
+    std::string msg;
+    uint32_t root_depth = 0;
+
+    void fail(int code, const std::string& m) { if (err == RTP_OK) { err = code; msg = m; } }
+
+    bool check(const rtp_hittable* h, bool in_nested, uint32_t index) {
+        if (h->kind == RTP_HITTABLE_SPHERE) { if (h->material >= d->n_materials) { fail(RTP_ERR_INVALID, "sphere material out of range"); return false; } }
+        else if (h->kind == RTP_HITTABLE_TRIANGLE) {
+            if (h->mesh >= d->n_meshes || static_cast<uint64_t>(h->triangle) + 3 > d->meshes[h->mesh].n_indices) { fail(RTP_ERR_INVALID, "triangle id out of range"); return false; }
+        } else if (h->kind == RTP_HITTABLE_LIST || h->kind == RTP_HITTABLE_BVH) {
+            // a run of `nested`; a nested container's run lies entirely before the container itself, so nesting cannot cycle
+            if (static_cast<uint64_t>(h->mesh) + h->triangle > (in_nested ? index : d->n_nested)) { fail(RTP_ERR_INVALID, "nested run out of range"); return false; }
+            if (h->kind == RTP_HITTABLE_BVH && h->triangle == 0) { fail(RTP_ERR_INVALID, "Bvh::new on an empty list is unreachable!() in the reference (bvh.rs:40)"); return false; }
+        } else { fail(RTP_ERR_INVALID, "unknown hittable kind"); return false; }
+        return true;
+    }
+
+    // hittable.rs:27-34, 124-147; false where the reference panics (the box of a Bvh, hittable.rs:32)
+    bool bbox(const rtp_hittable* h, double* lo, double* hi) {
+        if (h->kind == RTP_HITTABLE_BVH) { fail(RTP_ERR_INVALID, "bounding box of a Bvh: \"Do not take the bounding box of a Bvh\" (hittable.rs:32)"); return false; }
+        if (h->kind == RTP_HITTABLE_LIST) {  // AABB::default() when empty, else a left fold of AABB::union (utility.rs:130-135)
+            for (int k = 0; k < 3; ++k) lo[k] = hi[k] = 0.0;
+            const rtp_hittable* items = d->nested + h->mesh;
+            for (uint32_t i = 0; i < h->triangle; ++i) {
+                double a[3], b[3];
+                if (!bbox(&items[i], a, b)) return false;
+                for (int k = 0; k < 3; ++k) { lo[k] = i ? min_num(lo[k], a[k]) : a[k]; hi[k] = i ? max_num(hi[k], b[k]) : b[k]; }
+            }
+            return true;
+        }
+        if (h->kind == RTP_HITTABLE_SPHERE) {
+            for (int k = 0; k < 3; ++k) { lo[k] = h->center[k] - h->radius; hi[k] = h->center[k] + h->radius; }
+            return true;
+        }
+        const rtp_mesh& m = d->meshes[h->mesh];
+        const double* a = m.vertices[m.indices[h->triangle + 0]].position;
+        const double* b = m.vertices[m.indices[h->triangle + 1]].position;
+        const double* c = m.vertices[m.indices[h->triangle + 2]].position;
+        for (int k = 0; k < 3; ++k) { lo[k] = min_num(min_num(a[k], b[k]), c[k]); hi[k] = max_num(max_num(a[k], b[k]), c[k]); }
+        return true;
+    }
+
+    // the primitives of `h` in evaluation order, all behind `gate` (nullptr: none)
+    void emit(const rtp_hittable* h, uint32_t top, const double* gate) {
+        if (err != RTP_OK) return;
+        if (h->kind == RTP_HITTABLE_LIST) {
+            const rtp_hittable* items = d->nested + h->mesh;
+            for (uint32_t i = 0; i < h->triangle; ++i) emit(&items[i], top, gate);
+        } else if (h->kind == RTP_HITTABLE_BVH) {
+            if (gate) { fail(RTP_ERR_INVALID, "a Bvh below a Bvh leaf: its bounding box is needed (hittable.rs:32 panics)"); return; }
+            emit_bvh(d->nested + h->mesh, h->triangle, false, top);
+        } else {
+            SeqPrim sp;
+            sp.h = h; sp.top = top; sp.gated = gate != nullptr;
+            for (int k = 0; k < 3; ++k) { sp.gmin[k] = gate ? gate[k] : 0.0; sp.gmax[k] = gate ? gate[3 + k] : 0.0; }
+            seq.push_back(sp);
+        }
+    }
+
+    // Bvh::new (bvh.rs:70-91) over `items`, then its leaves in depth-first order, each behind its own box
+    void emit_bvh(const rtp_hittable* items, uint32_t n, bool is_root, uint32_t top) {
+        std::vector<BuildItem> bi(n);
+        for (uint32_t i = 0; i < n && err == RTP_OK; ++i) {
+            bi[i].id = i;
+            if (!bbox(&items[i], bi[i].bmin, bi[i].bmax)) return;
+            for (int k = 0; k < 3; ++k) {
+                const double key = 0.5 * (bi[i].bmin[k] + bi[i].bmax[k]);
+                if (key != key) { fail(RTP_ERR_INVALID, "NaN bounding-box centroid (partial_cmp().unwrap() panics, bvh.rs:63)"); return; }
+            }
+        }
+        if (err != RTP_OK) return;
+        std::vector<DNode> tmp(static_cast<size_t>(2) * n - 1);
+        Builder b{bi, tmp};
+        b.build(0, n, 0, 0, 1, 0);
+        if (is_root) root_depth = b.depth.load();
+        for (uint32_t r = 0; r < n; ++r) {
+            double gate[6];
+            for (int k = 0; k < 3; ++k) { gate[k] = bi[r].bmin[k]; gate[3 + k] = bi[r].bmax[k]; }
+            emit(&items[bi[r].id], is_root ? bi[r].id : top, gate);
+        }
+    }
+};
+
 int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     if (!d || !out) return set_error(RTP_ERR_INVALID, "null scene description");
     if (d->abi_version != RTP_ABI_VERSION) return set_error(RTP_ERR_INVALID, "rtp_scene_desc.abi_version mismatch");
@@ -548,8 +651,34 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     }
 
     // ---- leaf boxes: hittable.rs:124-140 ---------------------------------------------------
-    const uint32_t n = d->n_hittables;
-    std::vector<BuildItem> items(n);
+    if (d->n_nested && !d->nested) return set_error(RTP_ERR_INVALID, "null nested table with non-zero count");
+    bool nested = false;
+    for (uint32_t i = 0; i < d->n_hittables && !nested; ++i) nested = d->hittables[i].kind >= RTP_HITTABLE_LIST;
+    uint32_t n = d->n_hittables;      // primitives of the flattened scene (more than n_hittables when containers are nested)
+    std::vector<BuildItem> items;     // per primitive slot: the box that gates it + the id reported for it
+    std::vector<const rtp_hittable*> prim_h;  // per primitive slot: its Sphere / Triangle description
+    std::vector<uint8_t> gated;       // nested List roots: the primitive sits behind a box (a leaf of a nested Bvh)
+    NestedFlattener nf{d};
+    if (nested) {
+        for (uint32_t i = 0; i < d->n_hittables; ++i) if (!nf.check(&d->hittables[i], false, i)) return set_error(nf.err, nf.msg);
+        for (uint32_t i = 0; i < d->n_nested; ++i) if (!nf.check(&d->nested[i], true, i)) return set_error(nf.err, nf.msg);
+        if (d->root_kind == RTP_ROOT_BVH) nf.emit_bvh(d->hittables, d->n_hittables, true, 0);
+        else for (uint32_t i = 0; i < d->n_hittables; ++i) nf.emit(&d->hittables[i], i, nullptr);
+        if (nf.err != RTP_OK) return set_error(nf.err, nf.msg);
+        if (nf.seq.size() >= kWideSlotMask) return set_error(RTP_ERR_INVALID, "too many primitives");
+        n = static_cast<uint32_t>(nf.seq.size());
+        if (d->root_kind == RTP_ROOT_BVH && n == 0) return set_error(RTP_ERR_UNSUPPORTED, "a Bvh whose leaves are all empty lists holds no primitive");
+        items.resize(n); prim_h.resize(n); gated.resize(n);
+        for (uint32_t k = 0; k < n; ++k) {
+            const SeqPrim& sp = nf.seq[k];
+            items[k].id = sp.top;
+            std::memcpy(items[k].bmin, sp.gmin, sizeof sp.gmin);
+            std::memcpy(items[k].bmax, sp.gmax, sizeof sp.gmax);
+            prim_h[k] = sp.h;
+            gated[k] = sp.gated ? 1 : 0;
+        }
+    } else {
+    items.resize(n);
     std::atomic<int> first_bad{0};
     std::string bad_msg;
     std::mutex bad_lock;
@@ -580,7 +709,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
                 it.bmax[k] = max_num(max_num(a[k], b[k]), c[k]);
             }
         } else {
-            { fail(RTP_ERR_UNSUPPORTED, "nested List/Bvh hittables are outside the hot path (DESIGN.md)"); return; }
+            { fail(RTP_ERR_INVALID, "unknown hittable kind"); return; }
         }
         if (d->root_kind == RTP_ROOT_BVH)
             for (int k = 0; k < 3; ++k) {
@@ -591,10 +720,25 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
       }
     });
     if (first_bad.load()) return set_error(first_bad.load(), bad_msg);
+    }
 
     // ---- tree ---------------------------------------------------------------------------------
     out->depth = 0;
-    if (d->root_kind == RTP_ROOT_BVH) {
+    if (d->root_kind == RTP_ROOT_BVH && nested) {
+        // the sequence is already in evaluation order (NestedFlattener); any binary tree over it is a valid culling tree as long
+        // as every gate box is ordered and finite, so the SAH-over-a-sequence builder is used directly
+        for (const BuildItem& it : items)
+            for (int k = 0; k < 3; ++k)
+                if (!(it.bmin[k] <= it.bmax[k]) || !std::isfinite(it.bmin[k]) || !std::isfinite(it.bmax[k]))
+                    return set_error(RTP_ERR_UNSUPPORTED, "nested containers together with an inverted or non-finite bounding box");
+        out->nodes.assign(static_cast<size_t>(2) * n - 1, DNode{});
+        out->depth = nf.root_depth;
+        out->n_reference_nodes = 2 * d->n_hittables - 1;
+        SeqBuilder sb{items, out->nodes};
+        sb.build(0, n, 0, 1, 4);
+        out->device_depth = sb.depth.load();
+        lap("nested containers flattened; SAH culling tree over the evaluation order");
+    } else if (d->root_kind == RTP_ROOT_BVH) {
         out->nodes.assign(static_cast<size_t>(2) * n - 1, DNode{});
         lap("tables, validation, leaf boxes");
         Builder b{items, out->nodes};
@@ -651,7 +795,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     parallel_chunks(n, [&](size_t lo_s, size_t hi_s) {
       for (uint32_t slot = static_cast<uint32_t>(lo_s); slot < hi_s; ++slot) {
         uint32_t id = items[slot].id;
-        const rtp_hittable& h = d->hittables[id];
+        const rtp_hittable& h = nested ? *prim_h[slot] : d->hittables[id];
         DPrim& p = out->prims[slot];
         DAttr& at = out->attrs[slot];
         std::memset(&p, 0, sizeof p);
@@ -689,7 +833,7 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     lap("primitive and attribute records");
     if (d->root_kind == RTP_ROOT_BVH) {
         for (DNode& nd : out->nodes)
-            if (nd.prim != kNoPrim) nd.kind = d->hittables[items[nd.prim].id].kind;
+            if (nd.prim != kNoPrim) nd.kind = nested ? prim_h[nd.prim]->kind : d->hittables[items[nd.prim].id].kind;
         build_wide(out->nodes, &out->wide, &out->wide_boxes, &out->wide_depth);
         lap("4-wide collapse");
         prepare_any_order(out);
@@ -699,7 +843,9 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
         out->nodes.assign(n ? n : 1, DNode{});
         for (uint32_t slot = 0; slot < n; ++slot) {
             DNode& nd = out->nodes[slot];
-            nd.skip = slot + 1; nd.prim = slot; nd.kind = d->hittables[slot].kind;
+            nd.skip = slot + 1; nd.prim = slot; nd.kind = nested ? prim_h[slot]->kind : d->hittables[slot].kind;
+            nd._pad = (nested && gated[slot]) ? 1u : 0u;  // the primitive sits behind the box in its DPrim (leaf of a nested Bvh): gate it first
+            if (nd._pad) out->list_gates = true;
         }
         if (n == 0) { out->nodes[0].skip = 1; out->nodes[0].prim = kNoPrim; }
     }

@@ -28,7 +28,7 @@ struct alignas(64) DNode {  // 64 B
     uint32_t skip;  // pre-order index of the next node once this subtree is done
     uint32_t prim;  // leaf: primitive slot (= DFS rank of the leaf); branch: kNoPrim
     uint32_t kind;  // leaf: rtp_hittable_kind
-    uint32_t _pad;
+    uint32_t _pad;  // List roots: 1 = test the box in DPrim first (a leaf of a nested Bvh), 0 = no gate (hittable.rs:110-120)
 };
 static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
 
@@ -143,6 +143,7 @@ struct FlatScene {
     uint32_t depth = 0;              // of the reference tree (bvh.rs), what rtp_scene_info reports
     uint32_t n_reference_nodes = 0;  // 2n-1
     uint32_t device_depth = 0;       // of the culling tree the kernels walk
+    bool list_gates = false;         // List root with nested Bvh items: some primitives are gated by a box (DNode::_pad)
     bool any_ok = false;             // the any-order walk may be used on this scene (prepare_any_order, rtp_host.cpp)
     std::vector<DWide> free_wide;    // second culling tree over the Morton order of the leaves (any-order walk of big scenes); may be empty
     std::vector<double> free_boxes;
