@@ -11,6 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # pytest-timeout is in the image; registering the marker keeps `--strict-markers` runs and plugin-less runs quiet
+    config.addinivalue_line("markers", "timeout(seconds): per-test limit (pytest-timeout; ignored when the plugin is absent)")
 
 
 @pytest.fixture(scope="session")

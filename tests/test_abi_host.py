@@ -47,7 +47,9 @@ def test_struct_layouts_match_the_header(tmp_path):
         ("rtp_material", "emit"): A.Material.emit.offset, ("rtp_texture", "rgba"): A.Texture.rgba.offset,
         ("rtp_scene_desc", "background"): A.SceneDesc.background.offset, ("rtp_camera", "position"): A.Camera.position.offset,
         ("rtp_render_params", "seed"): A.RenderParams.seed.offset, ("rtp_render_params", "flags"): A.RenderParams.flags.offset,
-        ("rtp_stats", "device_ms"): A.Stats.device_ms.offset, ("rtp_hit_full", "uv"): A.HIT_FULL_DTYPE.fields["uv"][1],
+        ("rtp_render_params", "device_mask"): A.RenderParams.device_mask.offset, ("rtp_render_params", "row_stride"): A.RenderParams.row_stride.offset,
+        ("rtp_scene_desc", "nested"): A.SceneDesc.nested.offset, ("rtp_scene_desc", "n_nested"): A.SceneDesc.n_nested.offset,
+        ("rtp_stats", "device_ms"): A.Stats.device_ms.offset, ("rtp_stats", "trace_ms"): A.Stats.trace_ms.offset, ("rtp_hit_full", "uv"): A.HIT_FULL_DTYPE.fields["uv"][1],
         ("rtp_hittable", "center"): A.HITTABLE_DTYPE.fields["center"][1],
     }
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
@@ -127,13 +129,13 @@ def test_scene_validation_errors():
     _bad(lambda s: setattr(s, "hittables", s.hittables[:0]))                  # Bvh::new(vec![]) is unreachable!() (bvh.rs:40)
     _bad(lambda s: s.hittables["center"].__setitem__(1, [np.nan, 0, 0]))      # partial_cmp().unwrap() (bvh.rs:63)
 
-    def nested(s):
-        s.hittables["kind"][0] = 2
+    _bad(lambda s: s.hittables["kind"].__setitem__(0, 9))                      # not a Hittable variant
+    # nested containers are accepted (tests/test_nested_hittables.py), their runs are validated
     sc = scenes.one_triangle()
-    nested(sc)
+    sc.hittables["kind"][0], sc.hittables["mesh"][0], sc.hittables["triangle"][0] = A.HITTABLE_LIST, 0, 4
     with pytest.raises(api.RtpError) as e:
         api.bvh_build_order(sc)
-    assert e.value.code == A.ERR_UNSUPPORTED
+    assert e.value.code == A.ERR_INVALID and "nested run" in str(e.value)
 
 
 def test_abi_version_is_checked():
@@ -237,3 +239,28 @@ def test_traversal_plan_of_scenes():
     mesh = api.Mesh.from_arrays(pos, indices=idx, material=0)
     _, info = api.bvh_build_order(scene_of(api.Hittable.triangles_of(mesh, 0), [mesh]))
     assert (info.any_order, info.n_big, info.n_leaves) == (1, 2, 146)
+
+
+def build_c_driver(tmp_path):
+    """tests/c_driver.c: a plain-C host of the boundary, compiled against include/rtp.h and linked with -lrtp_b200"""
+    lib_dir = os.path.dirname(A.LIB_PATH)
+    exe = tmp_path / "c_driver"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c_driver.c"), "-o", str(exe),
+                    "-L", lib_dir, "-lrtp_b200", f"-Wl,-rpath,{lib_dir}", "-lm"], check=True)
+    return exe
+
+
+def test_plain_c_driver_host_side(tmp_path):
+    """host-only entry points work from C; validation precedes the device; without a GPU the compute call is RTP_ERR_CUDA"""
+    exe = build_c_driver(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "host checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_driver_on_the_gpu(tmp_path):
+    exe = build_c_driver(tmp_path)
+    r = subprocess.run([str(exe), "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "GPU checks passed" in r.stdout
