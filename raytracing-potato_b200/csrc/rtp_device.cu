@@ -1192,8 +1192,22 @@ __global__ void __launch_bounds__(256) wave_generate_kernel(DCamera cam, DRender
     wq.state[0][p] = make_uint4(static_cast<uint32_t>(p), rng.k, rp.max_bounce, 0u);
 }
 
-__global__ void __launch_bounds__(256, 3) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch) {
-    const size_t n = static_cast<size_t>(wq.count[bounce]);
+// A ray trace_any_kernel did not answer inside the wavefront integrator (not eligible for the f32 walk, stack overflow, abnormal leaf in
+// the final window: a handful per frame at most) is marked in its hit record and traced here, by the thread that shades it, with the
+// exact f64 walk of bvh.rs:93-119 (closest_hit_bvh): no second traversal launch per bounce.
+constexpr uint32_t kDeferredHit = 0xFFFFFFFEu;
+__device__ __noinline__ void trace_deferred(const DSceneView& sc, D3 o, D3 d, HitRec& h) {
+    LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
+    h.t = CUDART_INF; h.u = 0.0; h.v = 0.0; h.kind = 0;
+    closest_hit_bvh<false>(sc, o, d, kRayEpsilon, h, lc);
+}
+
+// GEN0: this is segment 0 of a launch whose primary rays were never written to a queue (trace_any_kernel<.., GEN>): the thread
+// regenerates its path's camera ray (same draws, same bits) instead of reading 80 B of ray and state
+template <bool GEN0>
+__global__ void __launch_bounds__(256, 3) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch, DCamera cam,
+                                                            size_t n_gen) {
+    const size_t n = GEN0 ? n_gen : static_cast<size_t>(wq.count[bounce]);
     const int cur = bounce & 1, nxt = cur ^ 1;
     const unsigned lane = threadIdx.x & 31u;
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -1204,22 +1218,35 @@ __global__ void __launch_bounds__(256, 3) wave_shade_kernel(DSceneView sc, DRend
         D3 o = mk(0, 0, 0), d = mk(0, 0, 0);
         uint4 st = make_uint4(0, 0, 0, 0);
         if (q < n) {
-            const double2* rp2 = reinterpret_cast<const double2*>(wq.rays[cur] + q);
-            const double2 r0 = rp2[0], r1 = rp2[1], r2 = rp2[2];
-            o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
-            st = wq.state[cur][q];
+            if (GEN0) {
+                uint32_t gi, gj, gs;
+                path_coords(rp, q, gi, gj, gs);
+                Rng grng;
+                rng_init(grng, rp.seed, gj * rp.width + gi, gs, RTP_RNG_STREAM_PATH);
+                primary_ray(cam, rp, gi, gj, grng, o, d);
+                st = make_uint4(static_cast<uint32_t>(q), grng.k, rp.max_bounce, 0u);
+            } else {
+                const double2* rp2 = reinterpret_cast<const double2*>(wq.rays[cur] + q);
+                const double2 r0 = rp2[0], r1 = rp2[1], r2 = rp2[2];
+                o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
+                st = wq.state[cur][q];
+            }
             const double2* hp = reinterpret_cast<const double2*>(wq.hits + q);
             const double2 h0 = hp[0], h1 = hp[1];
-            const uint32_t slotkind = static_cast<uint32_t>(__double2loint(h1.y));
+            uint32_t slotkind = static_cast<uint32_t>(__double2loint(h1.y));
             uint32_t depth = st.z & 0xFFu, nb = (st.z >> 8) & 0xFFu, first_hit = (st.z >> 16) & 1u;
             const size_t p = st.x;
             D3 L = mk(0.0, 0.0, 0.0);
+            HitRec h;
+            h.t = h0.x; h.u = h0.y; h.v = h1.x; h.slot = slotkind & 0x7FFFFFFFu; h.kind = slotkind >> 31;
+            if (slotkind == kDeferredHit) {
+                trace_deferred(sc, o, d, h);
+                slotkind = h.slot == kNoPrim ? kNoPrim : 0u;
+            }
             if (slotkind == kNoPrim) {
                 L = shade_miss(sc, d);
             } else {
                 if (bounce == 0) first_hit = 1u;
-                HitRec h;
-                h.t = h0.x; h.u = h0.y; h.v = h1.x; h.slot = slotkind & 0x7FFFFFFFu; h.kind = slotkind >> 31;
                 uint32_t i, j, smp;
                 path_coords(rp, p, i, j, smp);
                 Rng rng;
@@ -1559,9 +1586,17 @@ __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D
 #ifndef RTP_ANY_STEPS
 #define RTP_ANY_STEPS 2   // walk steps per round of votes
 #endif
-template <bool COUNT, int OUT>
+// GEN (wavefront integrator, segment 0): ray i IS camera path i of the launch (main.rs:70-76: jitter, lens draw, Camera::shoot), made
+// here from (camera, frame parameters) instead of being read from a queue a generate kernel wrote: saves an 80 B/path round trip
+// through HBM and one launch per frame; wave_shade_kernel<GEN0> regenerates the same ray when it shades the vertex.
+struct GenArgs {
+    DCamera cam;
+    DRender rp;
+};
+
+template <bool COUNT, int OUT, bool GEN>
 __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out, Counters* counters,
-                                                           WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev, DeferList defer) {
+                                                           WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev, DeferList defer, GenArgs gen) {
     extern __shared__ __align__(16) uint32_t any_stack[];
     if (n_dev) n = static_cast<size_t>(*n_dev);
     const unsigned lane = threadIdx.x & 31u;
@@ -1639,8 +1674,13 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                 // the walk of this lane's ray is over. An abnormal leaf inside the final window: the answer may depend on the
                 // reference's visiting order, the in-order kernel decides (A_min was rounded down, T_win compared in f64: conservative)
                 if (A_min != CUDART_INF_F && static_cast<double>(A_min) <= T_win) {
-                    const unsigned long long slot = atomicAdd(defer.count, 1ull);
-                    defer.idx[slot] = idx;
+                    if (OUT == OUT_WAVE) {  // the thread that shades this vertex traces it with the exact walk (wave_shade_kernel)
+                        reinterpret_cast<double2*>(static_cast<WaveHit*>(out) + idx)[1] = make_double2(0.0, __hiloint2double(0, static_cast<int>(kDeferredHit)));
+                    } else {
+                        const unsigned long long slot = atomicAdd(defer.count, 1ull);
+                        defer.idx[slot] = idx;
+                        lc.rays--;  // the in-order kernel counts it
+                    }
                     if (COUNT) lc.rewalks++;
                 } else {
                     HitRec h;
@@ -1661,21 +1701,34 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                 const int rank = __popc(free_mask & lt_mask);
                 const size_t i = static_cast<size_t>(base) + rank;
                 if (!busy && rank < cnt && i < n) {
-                    const double* rp = reinterpret_cast<const double*>(rays + i);
-                    const double2 r0 = ldg_stream2(rp), r1 = ldg_stream2(rp + 2), r2 = ldg_stream2(rp + 4), r3 = ldg_stream2(rp + 6);
-                    o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
-                    tmin = r3.x;
-                    const double tmax = r3.y;
+                    double tmax;
+                    if (GEN) {
+                        uint32_t gi, gj, gs;
+                        path_coords(gen.rp, i, gi, gj, gs);
+                        Rng grng;
+                        rng_init(grng, gen.rp.seed, gj * gen.rp.width + gi, gs, RTP_RNG_STREAM_PATH);
+                        primary_ray(gen.cam, gen.rp, gi, gj, grng, o, d);
+                        tmin = kRayEpsilon; tmax = CUDART_INF;
+                    } else {
+                        const double* rp = reinterpret_cast<const double*>(rays + i);
+                        const double2 r0 = ldg_stream2(rp), r1 = ldg_stream2(rp + 2), r2 = ldg_stream2(rp + 4), r3 = ldg_stream2(rp + 6);
+                        o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
+                        tmin = r3.x; tmax = r3.y;
+                    }
                     inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
-                    lc.rays++;
                     // eligibility (walker_start + any_begin): finite origin, 1e-15 <= |1/d| <= 1e15 on every axis, |o| <= 1e15,
                     // 0 <= t_min <= t_max, self-consistent slack
                     bool ok = in_f32_range(inv.x) & in_f32_range(inv.y) & in_f32_range(inv.z) & (fabs(o.x) <= 1e15) & (fabs(o.y) <= 1e15) &
                               (fabs(o.z) <= 1e15) & (tmax >= tmin) & (tmin >= 0.0);
                     ok = ok & any_slack_of(sc, o, d, inv, tmin, s0f, s1f);
+                    if (ok || OUT == OUT_WAVE) lc.rays++;  // a ray deferred to the in-order kernel is counted there
                     if (!ok) {
-                        const unsigned long long slot = atomicAdd(defer.count, 1ull);
-                        defer.idx[slot] = static_cast<uint32_t>(i);
+                        if (OUT == OUT_WAVE) {
+                            reinterpret_cast<double2*>(static_cast<WaveHit*>(out) + i)[1] = make_double2(0.0, __hiloint2double(0, static_cast<int>(kDeferredHit)));
+                        } else {
+                            const unsigned long long slot = atomicAdd(defer.count, 1ull);
+                            defer.idx[slot] = static_cast<uint32_t>(i);
+                        }
                     } else {
                         idx = static_cast<uint32_t>(i);
                         sx = inv.x < 0.0; sy = inv.y < 0.0; sz = inv.z < 0.0;
@@ -1958,6 +2011,10 @@ struct DeviceScene {
     bool tail_offer = false;           // RTP_TAIL_OFFER
     size_t queue_budget_bytes = size_t(4) << 30;  // memory the integrator's per-launch buffers may take (set at upload from the free HBM)
     bool use_simple_render = false;    // RTP_RENDER_KERNEL=simple
+    bool no_fused_gen = true;          // RTP_FUSED_GEN=1: primary rays made inside the first traversal launch instead of by a generate kernel.
+                                       // Measured SLOWER (C1 2.01 vs 1.93 ms, C4 3.49 vs 3.39 ms/frame): the traversal kernel is bound by instruction
+                                       // issue, so ~250 more instructions per path (Philox, lens loop, normalise) in it and again in the shade kernel
+                                       // cost more than the 80 B/path round trip through HBM they save. Kept for A/B runs.
     bool debug_sync = false;           // RTP_DEBUG_SYNC
     double* frame = nullptr; size_t frame_elems = 0;
     uchar4* frame8 = nullptr; size_t frame8_elems = 0;  // RGBA8 output stage
@@ -2099,7 +2156,7 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
             ds->any_cap = std::max<uint32_t>(4u, std::min<uint32_t>(3u * any_depth + 1u, any_depth <= 12 ? 20u : 32u));
             if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = static_cast<uint32_t>(std::max(4, std::min(48, std::atoi(v))));  // tests
             ds->any_stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&any_per_sm, trace_any_kernel<false, OUT_HIT>, 128, ds->any_stack_bytes);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&any_per_sm, trace_any_kernel<false, OUT_HIT, false>, 128, ds->any_stack_bytes);
             ds->any_blocks = prop.multiProcessorCount * std::max(any_per_sm, 1);
             if (ds->use_combined) {
                 // the round-1 kernel: in-order entries live in the .x halves of the same uint2 columns, at least `depth` of them
@@ -2132,6 +2189,8 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         ds->use_simple_render = env && std::string(env) == "simple";
         env = std::getenv("RTP_DEBUG_SYNC");
         ds->debug_sync = env && std::atoi(env) != 0;
+        env = std::getenv("RTP_FUSED_GEN");
+        ds->no_fused_gen = !(env && std::atoi(env) != 0);
         if (const char* v = std::getenv("RTP_REFILL_MIN")) ds->tune.refill_min = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_PRIM_BATCH")) ds->tune.prim_batch = std::max(1, std::min(32, std::atoi(v)));
         if (const char* v = std::getenv("RTP_FAST_SLAB")) ds->tune.fast_slab = std::atoi(v) != 0;
@@ -2188,7 +2247,7 @@ static int debug_sync(const DeviceScene* ds, cudaStream_t st, const char* what, 
 }
 
 static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* d_out, int out_mode, bool count, Counters* counters,
-                        cudaStream_t stream, const unsigned long long* n_dev = nullptr, const TailArgs* tail = nullptr) {
+                        cudaStream_t stream, const unsigned long long* n_dev = nullptr, const TailArgs* tail = nullptr, const GenArgs* gen = nullptr) {
     if (n == 0) return RTP_OK;
     const unsigned block = 128;
     ds->last_trace_launches = 1;
@@ -2240,12 +2299,21 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         if (pure_any) {
             const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->any_blocks), want)));
             const DeferList defer{slot.defer_idx, slot.defer_count};
-#define RTP_LAUNCH_ANY(C, O) trace_any_kernel<C, O><<<g, block, ds->any_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, defer)
-            if (out_mode == OUT_FULL) { if (count) RTP_LAUNCH_ANY(true, OUT_FULL); else RTP_LAUNCH_ANY(false, OUT_FULL); }
-            else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_ANY(true, OUT_WAVE); else RTP_LAUNCH_ANY(false, OUT_WAVE); }
-            else { if (count) RTP_LAUNCH_ANY(true, OUT_HIT); else RTP_LAUNCH_ANY(false, OUT_HIT); }
+            const GenArgs ga = gen ? *gen : GenArgs{};
+#define RTP_LAUNCH_ANY(C, O, G) trace_any_kernel<C, O, G><<<g, block, ds->any_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, defer, ga)
+            if (out_mode == OUT_FULL) { if (count) RTP_LAUNCH_ANY(true, OUT_FULL, false); else RTP_LAUNCH_ANY(false, OUT_FULL, false); }
+            else if (out_mode == OUT_WAVE && gen) { if (count) RTP_LAUNCH_ANY(true, OUT_WAVE, true); else RTP_LAUNCH_ANY(false, OUT_WAVE, true); }
+            else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_ANY(true, OUT_WAVE, false); else RTP_LAUNCH_ANY(false, OUT_WAVE, false); }
+            else { if (count) RTP_LAUNCH_ANY(true, OUT_HIT, false); else RTP_LAUNCH_ANY(false, OUT_HIT, false); }
 #undef RTP_LAUNCH_ANY
             RTP_CUDA(cudaGetLastError());
+            if (out_mode == OUT_WAVE) {
+                // inside the integrator the (rare) rays this kernel does not answer are traced by the thread that shades them
+                RTP_CUDA(cudaEventRecord(slot.last_use, stream));
+                slot.used = true;
+                slot.stream = stream;
+                return RTP_OK;
+            }
             // the deferred rays (normally none: the launch then finds an empty list and leaves at once), in the reference's order
             const dim3 g2(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->inorder_blocks), want)));
 #define RTP_LAUNCH_DEFERRED(C, O) trace_persistent_kernel<C, O, false, 0><<<g2, block, ds->inorder_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, nullptr, ta, defer)
@@ -2475,10 +2543,17 @@ static int render_enqueue(DeviceScene* ds, const rtp_camera* camera, const rtp_r
         if (wave) {
             // generate -> (trace -> shade) x max_bounce; queue sizes stay on the device
             RTP_CUDA(cudaMemsetAsync(ds->wave.count, 0, 130 * sizeof(unsigned long long), st));
-            wave_generate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(cam, rp, ds->wave, total);
-            RTP_CUDA(cudaGetLastError());
-            ++launches;
-            { int rc = debug_sync(ds, st, "wave_generate_kernel", 0); if (rc != RTP_OK) return rc; }
+            // segment 0 without a generate kernel: the pure any-order kernel makes its primary rays itself (GenArgs) and the shade
+            // kernel regenerates them; other scenes (List roots, in-order walk) and tail-mode launches read them from queue 0
+            const bool fused_gen = ds->view.root_kind == RTP_ROOT_BVH && ds->any_order && !ds->use_combined && !ds->no_fused_gen &&
+                                   !(ds->tail_threshold && total <= ds->tail_threshold);
+            const GenArgs ga{cam, rp};
+            if (!fused_gen) {
+                wave_generate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(cam, rp, ds->wave, total);
+                RTP_CUDA(cudaGetLastError());
+                ++launches;
+                { int rc = debug_sync(ds, st, "wave_generate_kernel", 0); if (rc != RTP_OK) return rc; }
+            }
             const unsigned shade_grid = static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->shade_blocks), (total + 255) / 256));
             for (uint32_t b = 0; b < p->max_bounce; ++b) {
                 int rc;
@@ -2497,11 +2572,14 @@ static int render_enqueue(DeviceScene* ds, const rtp_camera* camera, const rtp_r
                     ++launches;
                     if (tail_certain) { if (want_stats) next_mark(ds, st); break; }
                 }
-                rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, ds->wave.count + b);
+                const bool gen0 = fused_gen && b == 0;
+                rc = launch_trace(ds, ds->wave.rays[b & 1], total, ds->wave.hits, OUT_WAVE, count, ds->counters, st, gen0 ? nullptr : ds->wave.count + b, nullptr,
+                                  gen0 ? &ga : nullptr);
                 if (rc != RTP_OK) return rc;
                 if (want_stats) next_mark(ds, st);
                 if ((rc = debug_sync(ds, st, "trace kernel <OUT_WAVE>", b)) != RTP_OK) return rc;
-                wave_shade_kernel<<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch);
+                if (gen0) wave_shade_kernel<true><<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch, cam, total);
+                else wave_shade_kernel<false><<<shade_grid, 256, 0, st>>>(ds->view, rp, ds->wave, b, ds->scratch, cam, 0);
                 RTP_CUDA(cudaGetLastError());
                 if ((rc = debug_sync(ds, st, "wave_shade_kernel", b)) != RTP_OK) return rc;
                 launches += ds->last_trace_launches + 1;
