@@ -1,7 +1,9 @@
-"""Multi-GPU host logic for the hot path (one process per GPU). The path shards without any data-path exchange:
-ray batches are sliced contiguously, frames are split by sample range (every rank renders the full tile rectangle for
-its own samples, into raw sums), and the only collective is one sum of the accumulation buffers at frame end — the
-reference's tile workers never communicate either (main.rs:61-92). `torch.distributed` is plumbing here."""
+"""Index helpers for hosts that run one process per GPU. The path shards without any data-path exchange: ray batches are
+sliced contiguously; frames are split either by ROWS (row_split: each rank renders all samples of its rows, rank 0 gathers
+them — bit-identical to one GPU, the split bench.py uses for strong scaling) or by SAMPLE RANGE (sample_range + raw sums +
+one sum at frame end). The reference's tile workers never communicate either (main.rs:61-92). A single process can instead
+hand all its GPUs to the library (rtp_scene_create_multi + rtp_render, include/rtp.h): that is where the multi-GPU
+implementation lives; `torch.distributed` here is plumbing for the per-process variant."""
 from typing import Tuple
 
 import numpy as np
@@ -18,6 +20,17 @@ def sample_range(num_samples: int, rank: int, world: int) -> Tuple[int, int]:
     """[sample_begin, sample_end) of `rank` out of num_samples per pixel. Samples are keyed by (pixel, sample) in the random
     stream, so the union over ranks is exactly the sample set of a single-GPU render."""
     return ray_slice(num_samples, rank, world)
+
+
+def row_split(rank: int, world: int) -> Tuple[int, int]:
+    """(row_offset, row_stride) of `rank` for rtp_render_params: the rows of the tile rectangle are dealt out round-robin, every
+    rank renders ALL samples of its rows, so gathering the rows gives the single-GPU frame bit for bit (no sum across ranks)."""
+    return rank, world
+
+
+def rows_of(height: int, rank: int, world: int) -> int:
+    """number of rows of a `height`-row rectangle that fall to `rank` under row_split"""
+    return (height - rank + world - 1) // world if rank < height else 0
 
 
 def reduce_frame(acc, group=None):

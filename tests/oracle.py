@@ -210,11 +210,11 @@ class Scene:
         out["leaf"], out["material"], out["t"] = f["leaf"], f["material"], f["t"]
         return out
 
-    def render(self, width, height, num_samples, max_bounce=8, seed=1, camera=None, sample_range=None, tile=None, flags=0, threads=None):
+    def render(self, width, height, num_samples, max_bounce=8, seed=1, camera=None, sample_range=None, tile=None, flags=0, threads=None, rows=None):
         cam = camera or self.camera
         cam = api.Camera(width / height, cam.fov, cam.focal_dist, cam.lens_radius, cam.transformation)
         p = api.render_params(width, height, num_samples, max_bounce, seed,
-                              sample_range[0] if sample_range else 0, sample_range[1] if sample_range else None, tile, flags)
+                              sample_range[0] if sample_range else 0, sample_range[1] if sample_range else None, tile, flags, rows)
         rgbf = np.zeros((height, width, 3), dtype=np.float64)
         fg = np.zeros((height, width), dtype=np.float64)
         st = A.Stats()

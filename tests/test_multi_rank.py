@@ -27,6 +27,10 @@ def test_slices_partition_exactly():
             assert max(sizes) - min(sizes) <= 1
     assert [rdist.sample_range(16, r, 8) for r in range(8)] == [(2 * r, 2 * r + 2) for r in range(8)]
     assert [rdist.sample_range(3, r, 2) for r in range(2)] == [(0, 2), (2, 3)]
+    for h in (1, 2, 7, 1080):
+        for world in (1, 2, 3, 8):
+            assert sum(rdist.rows_of(h, r, world) for r in range(world)) == h
+            assert all(rdist.rows_of(h, r, world) == len(range(h)[r::world]) for r in range(world))
 
 
 def _worker(rank, world, port, tmp):
@@ -51,6 +55,12 @@ def _worker(rank, world, port, tmp):
         rgb, fg, _ = o.render(w, h, spp, seed=9, sample_range=(sb, se), flags=A.RENDER_RAW_SUMS)
         acc = torch.from_numpy(np.concatenate([rgb.reshape(-1), fg.reshape(-1)]))
         rdist.reduce_frame(acc)
+        # --- frame: rows dealt out round-robin, every rank renders all samples of its rows, rank 0 gathers: no sum at all ---
+        ro, rs = rdist.row_split(rank, world)
+        rrgb, rfg, rst = o.render(w, h, spp, seed=9, rows=(ro, rs))
+        assert rst.paths == rdist.rows_of(h, rank, world) * w * spp
+        rows = [None] * world
+        dist.all_gather_object(rows, (rrgb[ro::rs].tobytes(), rfg[ro::rs].tobytes()))
         if rank == 0:
             full_hits = o.hit(rays)
             assert b"".join(parts) == full_hits.tobytes()
@@ -59,6 +69,12 @@ def _worker(rank, world, port, tmp):
             # the per-pixel sum is re-associated across ranks: a few ulp at most
             assert np.allclose(img, ref, rtol=1e-14, atol=1e-15)
             assert np.array_equal(acc[w * h * 3:].numpy().reshape(h, w) / spp, ref_fg)
+            by_rows = np.zeros_like(ref)
+            by_rows_fg = np.zeros_like(ref_fg)
+            for r in range(world):
+                by_rows[r::world] = np.frombuffer(rows[r][0], dtype=np.float64).reshape(-1, w, 3)
+                by_rows_fg[r::world] = np.frombuffer(rows[r][1], dtype=np.float64).reshape(-1, w)
+            assert by_rows.tobytes() == ref.tobytes() and by_rows_fg.tobytes() == ref_fg.tobytes()  # bit-identical
             open(os.path.join(tmp, "ok"), "w").write("ok")
     finally:
         dist.destroy_process_group()
