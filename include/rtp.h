@@ -389,6 +389,12 @@ int rtp_rng_draws(uint64_t seed, uint32_t index_lo, uint32_t index_hi, uint32_t 
 
 /* ---------------------------------------------------------------- diagnostics ----------- */
 
+/* Structural digests of a scene's device-resident build, read back from its first device: [0] the exact binary culling tree
+ * (pre-order boxes, skip pointers, leaf slots), [1] primitive and attribute records in rank order, [2] the 4-wide culling tree,
+ * hashed from the root down so that the numbering of its nodes does not matter, [3] number of 4-wide nodes | levels << 32.
+ * Two builds of the same description (host build, device build: RTP_DEVICE_BUILD) must agree in all four. Tests only. */
+int rtp_scene_digest(const rtp_scene* scene, uint64_t digest_out[4]);
+
 /* Measured f64 instruction throughput of the bound device, in 1e9 unfused f64 operations (DMUL or DADD, the
  * only kind the path executes: the reference never contracts a*b+c) per second: the denominator of the
  * FP64 figure in bench.py's roofline (SURVEY.md 8d asks for a measured peak). Runs for a few ms. */

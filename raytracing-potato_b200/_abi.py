@@ -205,6 +205,7 @@ PROTOTYPES = {
     "rtp_trace_camera": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rtp_rng_draws": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "rtp_probe_fp64": (C.c_int, [C.POINTER(C.c_double)]),
+    "rtp_scene_digest": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
 }
 
 # RTP_B200_LIB: another build of the same library (kernel A/B runs from tools/); it is still this product's CUDA library

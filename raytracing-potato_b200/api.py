@@ -545,6 +545,12 @@ class Scene:
     def handle(self):
         return self._h
 
+    def digest(self):
+        """structural digests of the device-resident build (rtp_scene_digest): equal for equal trees, whatever built them"""
+        out = (C.c_uint64 * 4)()
+        _check(self._lib, self._lib.rtp_scene_digest(self._h, out))
+        return tuple(int(x) for x in out)
+
     def devices(self) -> int:
         """bit d set = the scene holds a replica on CUDA device d"""
         m = C.c_uint32(0)

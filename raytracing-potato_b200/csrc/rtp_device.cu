@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "rtp_internal.h"
@@ -1950,6 +1951,7 @@ struct DeviceScene {
     int device = 0;
     DNode* nodes = nullptr;
     DWide* wide = nullptr;
+    size_t n_wide = 0;
     double* wide_boxes = nullptr;
     DWide* free_wide = nullptr;        // order-free culling tree of a big scene (any-order lanes), or nullptr
     double* free_boxes = nullptr;
@@ -2089,9 +2091,24 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
     DeviceScene* ds = new DeviceScene();
     ds->device = device;
     auto bail = [&](int code) { device_scene_free(ds); return code; };
+    // arrays built on a device (rtp_build.cu) are adopted there and copied peer to peer elsewhere; host-built ones are uploaded
+    auto take = [&](auto** dst, auto* src, size_t count) -> int {
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dst)>>;
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
+        if (count) RTP_CUDA(cudaMemcpyPeer(*dst, device, src, flat.dev.device, count * sizeof(T)));
+        ds->bytes += bytes;
+        return RTP_OK;
+    };
+    if (flat.dev.valid) {
+        if ((rc = take(&ds->nodes, flat.dev.nodes, flat.dev.n_nodes)) != RTP_OK) return bail(rc);
+        if ((rc = take(&ds->wide, flat.dev.wide, flat.dev.n_wide)) != RTP_OK) return bail(rc);
+        if ((rc = take(&ds->wide_boxes, flat.dev.wide_boxes, flat.dev.n_wide * 24)) != RTP_OK) return bail(rc);
+    } else {
     if ((rc = upload(flat.nodes, &ds->nodes, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide, &ds->wide, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.wide_boxes, &ds->wide_boxes, &ds->bytes)) != RTP_OK) return bail(rc);
+    }
     if (!flat.free_wide.empty()) {
         if ((rc = upload(flat.free_wide, &ds->free_wide, &ds->bytes)) != RTP_OK) return bail(rc);
         if ((rc = upload(flat.free_boxes, &ds->free_boxes, &ds->bytes)) != RTP_OK) return bail(rc);
@@ -2103,17 +2120,22 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         // RTP_TRAVERSAL=any | inorder overrides the choice
         const char* tv = std::getenv("RTP_TRAVERSAL");
         const bool f32_ok = flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96 &&
-                            flat.wide.size() < (size_t(1) << 28) && flat.free_wide.size() < (size_t(1) << 28);  // trace_any_kernel indexes nodes as 32-bit float4 offsets
+                            flat.wide_count() < (size_t(1) << 28) && flat.free_wide.size() < (size_t(1) << 28);  // trace_any_kernel indexes nodes as 32-bit float4 offsets
         bool want = true;  // every eligible scene takes the any-order walk by default (measured faster from the 4,969-leaf bunny up)
         if (tv && std::string(tv) == "any") want = true;
         if (tv && std::string(tv) == "inorder") want = false;
         if (const char* v = std::getenv("RTP_F32_CULLING")) if (std::atoi(v) == 0) want = false;
         // scenes that live in HBM rather than in the caches run the spill-free 4-blocks-per-SM build of the kernel
-        ds->any_order = (want && flat.any_ok && f32_ok) ? (flat.prims.size() >= kAnyOrderBigScene ? 2 : 1) : 0;
+        ds->any_order = (want && flat.any_ok && f32_ok) ? (flat.prim_count() >= kAnyOrderBigScene ? 2 : 1) : 0;
         if (const char* v = std::getenv("RTP_ANY_VARIANT")) if (ds->any_order) ds->any_order = std::atoi(v) == 2 ? 2 : 1;
     }
+    if (flat.dev.valid) {
+        if ((rc = take(&ds->prims, flat.dev.prims, flat.dev.n_prims)) != RTP_OK) return bail(rc);
+        if ((rc = take(&ds->attrs, flat.dev.attrs, flat.dev.n_prims)) != RTP_OK) return bail(rc);
+    } else {
     if ((rc = upload(flat.prims, &ds->prims, &ds->bytes)) != RTP_OK) return bail(rc);
     if ((rc = upload(flat.attrs, &ds->attrs, &ds->bytes)) != RTP_OK) return bail(rc);
+    }
     if ((rc = upload(flat.materials, &ds->materials, &ds->bytes)) != RTP_OK) return bail(rc);
     std::vector<DTexture> tex = flat.textures;
     ds->images.assign(tex.size(), nullptr);
@@ -2204,12 +2226,13 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ds->render_done, cudaEventDisableTiming);
     if (e != cudaSuccess) return bail(set_error(RTP_ERR_CUDA, std::string("scene resources: ") + cudaGetErrorString(e)));
 
+    ds->n_wide = flat.wide_count();
     DSceneView& v = ds->view;
     v.nodes = ds->nodes; v.wide = ds->wide; v.wide_boxes = ds->wide_boxes; v.prims = ds->prims;
     v.any_wide = ds->free_wide ? ds->free_wide : ds->wide; v.any_boxes = ds->free_wide ? ds->free_boxes : ds->wide_boxes;
     v.f32_culling = (flat.root_kind == RTP_ROOT_BVH && flat.boxes_finite && flat.scene_mag <= 1e15 && flat.wide_depth <= 96) ? 1u : 0u; v.attrs = ds->attrs; v.materials = ds->materials; v.textures = ds->textures;
-    v.n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.nodes.size()) : 0u;
-    v.n_prims = static_cast<uint32_t>(flat.prims.size());
+    v.n_nodes = flat.root_kind == RTP_ROOT_BVH ? static_cast<uint32_t>(flat.node_count()) : 0u;
+    v.n_prims = static_cast<uint32_t>(flat.prim_count());
     v.root_kind = flat.root_kind;
     v.bg_kind = flat.background.kind; v.bg_texture = flat.background.texture;
     v.any_order = ds->any_order ? 1u : 0u;
@@ -2677,6 +2700,76 @@ int rtp_init(int device) {
     return RTP_OK;
 }
 
+int rtp_scene_digest(const rtp_scene* scene, uint64_t digest_out[4]) {
+    if (!scene || !digest_out || !scene->dev) return set_error(RTP_ERR_INVALID, "null argument");
+    const DeviceScene* ds = scene->dev;
+    RTP_CUDA(cudaSetDevice(ds->device));
+    const size_t n_nodes = ds->view.n_nodes, n_prims = ds->view.n_prims, n_wide = ds->n_wide;
+    auto fnv = [](uint64_t h, const void* p, size_t bytes) {
+        const unsigned char* b = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
+        return h;
+    };
+    try {
+        std::vector<DNode> nodes(n_nodes);
+        if (n_nodes) RTP_CUDA(cudaMemcpy(nodes.data(), ds->nodes, n_nodes * sizeof(DNode), cudaMemcpyDeviceToHost));
+        uint64_t h0 = 0xCBF29CE484222325ull;
+        // the sign of a zero coordinate is not part of the tree: IEEE minNum / maxNum may return either of -0.0 and +0.0 (libm's
+        // fmin and the device's differ), and no slab test can tell them apart; x + 0.0 maps both to +0.0. _pad is build-private.
+        for (const DNode& nd : nodes) {
+            double box[6];
+            for (int k = 0; k < 3; ++k) { box[k] = nd.bmin[k] + 0.0; box[3 + k] = nd.bmax[k] + 0.0; }
+            h0 = fnv(h0, box, 48); h0 = fnv(h0, &nd.skip, 12);
+        }
+        std::vector<DNode>().swap(nodes);
+        uint64_t h1 = 0xCBF29CE484222325ull;
+        {
+            std::vector<DPrim> prims(n_prims);
+            if (n_prims) RTP_CUDA(cudaMemcpy(prims.data(), ds->prims, n_prims * sizeof(DPrim), cudaMemcpyDeviceToHost));
+            h1 = fnv(h1, prims.data(), n_prims * sizeof(DPrim));
+        }
+        {
+            std::vector<DAttr> attrs(n_prims);
+            if (n_prims) RTP_CUDA(cudaMemcpy(attrs.data(), ds->attrs, n_prims * sizeof(DAttr), cudaMemcpyDeviceToHost));
+            h1 = fnv(h1, attrs.data(), n_prims * sizeof(DAttr));
+        }
+        std::vector<DWide> wide(n_wide);
+        if (n_wide) RTP_CUDA(cudaMemcpy(wide.data(), ds->wide, n_wide * sizeof(DWide), cudaMemcpyDeviceToHost));
+        // post-order over the tree from node 0: a node's hash folds its planes, its mask and, per child, the leaf word or the child's hash
+        std::vector<uint64_t> hash(n_wide, 0);
+        std::vector<uint8_t> done(n_wide, 0);
+        std::vector<uint32_t> stack;
+        uint32_t levels = 0;
+        std::vector<uint32_t> depth_of(n_wide, 0);
+        if (n_wide) { stack.push_back(0); depth_of[0] = 1; }
+        while (!stack.empty()) {
+            const uint32_t i = stack.back();
+            bool ready = true;
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = wide[i].child[k];
+                if (!(c & kWideLeaf) && !done[c]) { if (c >= n_wide) return set_error(RTP_ERR_INVALID, "4-wide tree: child index out of range"); depth_of[c] = depth_of[i] + 1; stack.push_back(c); ready = false; }
+            }
+            if (!ready) continue;
+            stack.pop_back();
+            float planes[24];
+            for (int k = 0; k < 24; ++k) planes[k] = (&wide[i].plane[0][0][0])[k] + 0.0f;
+            uint64_t h = fnv(0xCBF29CE484222325ull, planes, sizeof planes);
+            h = fnv(h, &wide[i].big_mask, 4);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = wide[i].child[k];
+                const uint64_t v = (c & kWideLeaf) ? static_cast<uint64_t>(c) : hash[c];
+                h = fnv(h, &v, 8);
+            }
+            hash[i] = h; done[i] = 1;
+            levels = std::max(levels, depth_of[i]);
+        }
+        digest_out[0] = h0; digest_out[1] = h1; digest_out[2] = n_wide ? hash[0] : 0; digest_out[3] = static_cast<uint64_t>(n_wide) | (static_cast<uint64_t>(levels) << 32);
+    } catch (const std::exception& e) {
+        return set_error(RTP_ERR_NOMEM, e.what());
+    }
+    return RTP_OK;
+}
+
 int rtp_probe_fp64(double* gops_out) {
     if (!gops_out) return set_error(RTP_ERR_INVALID, "null argument");
     int rc = require_device();
@@ -2725,7 +2818,7 @@ static int scene_create_impl(const rtp_scene_desc* desc, uint32_t device_mask, r
     *out = nullptr;
     try {
         rtp_scene* s = new rtp_scene();
-        auto bail = [&](int code) { for (DeviceScene* ds : s->devs) { cudaSetDevice(ds->device); device_scene_free(ds); } delete s; return code; };
+        auto bail = [&](int code) { for (DeviceScene* ds : s->devs) { cudaSetDevice(ds->device); device_scene_free(ds); } device_free_arrays(&s->flat.dev); delete s; return code; };
         int rc = RTP_OK;
         if (device_mask) {
             for (int d = 0; d < 32 && rc == RTP_OK; ++d)
@@ -2751,7 +2844,8 @@ static int scene_create_impl(const rtp_scene_desc* desc, uint32_t device_mask, r
         if (rc != RTP_OK) return bail(rc);
         s->dev = s->devs[0];
         cudaSetDevice(s->dev->device);
-        s->n_leaves = static_cast<uint32_t>(s->flat.prims.size());
+        s->n_leaves = static_cast<uint32_t>(s->flat.prim_count());
+        device_free_arrays(&s->flat.dev);  // every replica holds its own copy now
         s->n_nodes = s->flat.root_kind == RTP_ROOT_BVH ? s->flat.n_reference_nodes : 0u;
         // the host copies of the big arrays are no longer needed
         std::vector<DNode>().swap(s->flat.nodes);
@@ -2813,7 +2907,7 @@ int rtp_bvh_build_order(const rtp_scene_desc* desc, uint32_t* leaf_ids_out, size
             std::copy(flat.leaf_order.begin(), flat.leaf_order.end(), leaf_ids_out);
         }
         if (info) {
-            info->n_leaves = static_cast<uint32_t>(flat.prims.size());
+            info->n_leaves = static_cast<uint32_t>(flat.prim_count());
             info->n_nodes = flat.root_kind == RTP_ROOT_BVH ? flat.n_reference_nodes : 0u;
             info->depth = flat.depth; info->root_kind = flat.root_kind; info->device_bytes = 0;
             info->culling_depth = flat.root_kind == RTP_ROOT_BVH ? flat.wide_depth : 0u;

@@ -143,26 +143,25 @@ struct SeqBuilder {
         }
     };
 
-    // split position k in [1, n-1] minimising area(L)*|L| + area(R)*|R|; ranges above kExact leaves are scanned at
-    // kChunks equally spaced candidates so the build stays O(n log n)
-    static constexpr size_t kExact = 4096, kChunks = 256;
+    // split position k in [1, n-1] minimising area(L)*|L| + area(R)*|R|, the FIRST minimum (strict <); no finite cost: n / 2.
+    // One backward sweep for the suffix areas, one forward sweep for the costs: O(n) per range, O(n log n) per tree. The device
+    // build (rtp_build.cu sah_cost_kernel) evaluates the same expression at every position, so both trees are equal node for node.
     size_t choose_split(size_t lo, size_t n) const {
-        const size_t step = n <= kExact ? 1 : (n + kChunks - 1) / kChunks;
-        const size_t m = (n + step - 1) / step;  // number of groups
-        std::vector<double> suffix(m + 1, 0.0);
+        thread_local std::vector<double> suffix;
+        suffix.assign(n + 1, 0.0);
         Box b;
         b.reset();
-        for (size_t g = m; g-- > 1;) {  // suffix[g] = area of groups g..m-1
-            for (size_t i = lo + g * step; i < std::min(lo + (g + 1) * step, lo + n); ++i) b.grow(items[i].bmin, items[i].bmax);
+        for (size_t g = n; g-- > 1;) {  // suffix[g] = area of leaves g..n-1
+            b.grow(items[lo + g].bmin, items[lo + g].bmax);
             suffix[g] = b.half_area();
         }
         b.reset();
         double best = std::numeric_limits<double>::infinity();
         size_t best_k = n / 2;
-        for (size_t g = 0; g + 1 < m; ++g) {
-            for (size_t i = lo + g * step; i < lo + (g + 1) * step; ++i) b.grow(items[i].bmin, items[i].bmax);
-            const size_t k = (g + 1) * step;
-            const double cost = b.half_area() * static_cast<double>(k) + suffix[g + 1] * static_cast<double>(n - k);
+        for (size_t g = 0; g + 1 < n; ++g) {
+            b.grow(items[lo + g].bmin, items[lo + g].bmax);
+            const size_t k = g + 1;
+            const double cost = b.half_area() * static_cast<double>(k) + suffix[k] * static_cast<double>(n - k);
             if (cost < best) { best = cost; best_k = k; }
         }
         return best_k;
@@ -659,6 +658,19 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
     std::vector<const rtp_hittable*> prim_h;  // per primitive slot: its Sphere / Triangle description
     std::vector<uint8_t> gated;       // nested List roots: the primitive sits behind a box (a leaf of a nested Bvh)
     NestedFlattener nf{d};
+    // Big flat Bvh scenes are built on the device from here on (rtp_build.cu device_build_scene): leaf boxes, reference order, SAH
+    // culling tree, records, 4-wide collapse and the any-order tables never exist on the host. RTP_DEVICE_BUILD: "0" never,
+    // "1" always (tests compare both builds), unset: scenes of >= 65,536 leaves.
+    if (device_build && !nested && d->root_kind == RTP_ROOT_BVH && n >= 2 && !(std::getenv("RTP_TREE") && std::string(std::getenv("RTP_TREE")) == "reference")) {
+        const char* dev_env = std::getenv("RTP_DEVICE_BUILD");
+        if (dev_env ? std::atoi(dev_env) != 0 : n >= 65536u) {
+            lap("tables and validation");
+            const int rc = device_build_scene(d, out, timing);
+            if (rc == RTP_OK) { lap("device build"); return RTP_OK; }
+            if (rc != 1) return rc;
+            // 1: not applicable (inverted or non-finite boxes): the host path below keeps the reference topology for such scenes
+        }
+    }
     if (nested) {
         for (uint32_t i = 0; i < d->n_hittables; ++i) if (!nf.check(&d->hittables[i], false, i)) return set_error(nf.err, nf.msg);
         for (uint32_t i = 0; i < d->n_nested; ++i) if (!nf.check(&d->nested[i], true, i)) return set_error(nf.err, nf.msg);
@@ -742,8 +754,8 @@ int flatten_scene(const rtp_scene_desc* d, FlatScene* out, bool device_build) {
         out->nodes.assign(static_cast<size_t>(2) * n - 1, DNode{});
         lap("tables, validation, leaf boxes");
         Builder b{items, out->nodes};
-        const char* dev_env = std::getenv("RTP_DEVICE_BUILD");  // "0": never, "1": always, unset: scenes of >= 65,536 leaves
-        const bool on_device = device_build && (dev_env ? std::atoi(dev_env) != 0 : n >= 65536u);
+        const char* dev_env = std::getenv("RTP_DEVICE_ORDER");  // "1": only the reference ORDER on the device (round 1's first stage; tests keep it alive)
+        const bool on_device = device_build && dev_env && std::atoi(dev_env) != 0;
         if (on_device) {
             // bvh.rs:36-67 on the GPU: one segmented sort of all leaves per depth (rtp_build.cu), then the boxes bottom-up here
             std::vector<double> boxes(static_cast<size_t>(n) * 6);

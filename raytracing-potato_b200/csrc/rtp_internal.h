@@ -128,7 +128,21 @@ constexpr uint32_t kMaxBig = 8;
 // ---------------------------------------------------------------------------------------------
 // Host-side flattened scene produced by rtp_host.cpp and uploaded by rtp_device.cu
 // ---------------------------------------------------------------------------------------------
+// Big arrays that were BUILT on a device (rtp_build.cu device_build_scene) and never existed on the host: device_scene_upload
+// adopts them on that device and copies them peer to peer to the other devices of a multi-device scene.
+struct DevArrays {
+    bool valid = false;
+    int device = -1;
+    DNode* nodes = nullptr; size_t n_nodes = 0;
+    DWide* wide = nullptr; double* wide_boxes = nullptr; size_t n_wide = 0;
+    DPrim* prims = nullptr; DAttr* attrs = nullptr; size_t n_prims = 0;
+};
+
 struct FlatScene {
+    DevArrays dev;
+    size_t prim_count() const { return dev.valid ? dev.n_prims : prims.size(); }
+    size_t node_count() const { return dev.valid ? dev.n_nodes : nodes.size(); }
+    size_t wide_count() const { return dev.valid ? dev.n_wide : wide.size(); }
     std::vector<DNode> nodes;
     std::vector<DWide> wide;
     std::vector<double> wide_boxes;
@@ -169,6 +183,13 @@ int flatten_scene(const rtp_scene_desc* desc, FlatScene* out, bool device_build 
 struct DeviceScene;
 int ensure_device();  // binds device 0 if rtp_init has not been called; RTP_ERR_CUDA without a usable sm_100 GPU
 int device_reference_order(const double* boxes /* n x {min xyz, max xyz} */, uint32_t n, uint32_t* order_out /* item index by DFS rank */);
+int device_reference_order_dev(const double* d_boxes, uint32_t n, uint32_t* d_order_out);  // the same with device pointers
+// The whole of flatten_scene's geometry part on the current device for a flat (un-nested) Bvh scene: leaf boxes, the reference's
+// depth-first order, the SAH culling tree over that order, primitive / attribute records, the 4-wide collapse and the any-order
+// tables. Fills out->dev and the host-side metadata. Returns RTP_OK, a negative status, or 1 = "not applicable, use the host
+// path" (irregular boxes). `timing`: phase times on stderr.
+int device_build_scene(const rtp_scene_desc* d, FlatScene* out, bool timing);
+void device_free_arrays(DevArrays* a);
 int device_scene_upload(const FlatScene& flat, int device /* < 0: the bound device */, DeviceScene** out);
 void device_scene_free(DeviceScene* ds);
 uint64_t device_scene_bytes(const DeviceScene* ds);

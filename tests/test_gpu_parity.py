@@ -492,6 +492,13 @@ def test_device_bvh_order_equals_reference_order(gpu, monkeypatch, name):
     gh = api.Scene(sc)
     o = oracle.Scene(sc)
     assert (g.leaf_order() == o.leaf_order()).all() and (gh.leaf_order() == o.leaf_order()).all()
+    # the whole build runs on the device now (leaf boxes, order, SAH culling tree, records, 4-wide collapse, any-order tables):
+    # equal to the host build node for node and record for record (rtp_scene_digest), with the same plan
+    assert g.digest() == gh.digest(), (g.digest(), gh.digest())
+    ig, ih = g.info(), gh.info()
+    for f in ("n_leaves", "n_nodes", "depth", "culling_depth", "n_big"):
+        assert getattr(ig, f) == getattr(ih, f), f
+    assert (ig.any_order != 0) == (ih.any_order != 0)
     cam = api.Camera(1.0, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
     rays = oracle.camera_rays(cam, 96, 96)
     assert_hits_equal_bits(g.hit(rays), o.hit(rays))
