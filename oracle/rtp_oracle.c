@@ -283,22 +283,46 @@ static int item_cmp(const void* pa, const void* pb, void* arg) {
     return (a->id > b->id) - (a->id < b->id);
 }
 
-/* bvh.rs:36-56 make_bvh: children are pushed before their parent */
-static uint32_t make_bvh(orc_scene* s, orc_item* items, size_t n, int axis, uint32_t depth) {
-    if (depth > s->depth) s->depth = depth;
+/* bvh.rs:36-56 make_bvh: children are pushed before their parent, so the subtree over n leaves fills the 2n-1 consecutive node
+ * slots starting at `base` (left subtree, right subtree, then the node itself): the numbering of the reference's sequential
+ * `nodes.push`. Because the slots are known up front, the two halves of a big range are built on two threads (test
+ * infrastructure for the 10 M-leaf scene; the result does not depend on it). */
+typedef struct {
+    orc_scene* s; orc_item* items; size_t n; int axis; uint32_t depth, base, spawn;
+} bvh_job;
+static uint32_t make_bvh_at(orc_scene* s, orc_item* items, size_t n, int axis, uint32_t depth, uint32_t base, uint32_t spawn);
+static void* bvh_job_run(void* arg) {
+    bvh_job* j = (bvh_job*)arg;
+    make_bvh_at(j->s, j->items, j->n, j->axis, j->depth, j->base, j->spawn);
+    return NULL;
+}
+static uint32_t make_bvh_at(orc_scene* s, orc_item* items, size_t n, int axis, uint32_t depth, uint32_t base, uint32_t spawn) {
+    uint32_t seen = __atomic_load_n(&s->depth, __ATOMIC_RELAXED);
+    while (depth > seen && !__atomic_compare_exchange_n(&s->depth, &seen, depth, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    const uint32_t self = base + (uint32_t)(2 * n - 2);
     if (n == 1) {
-        orc_node* nd = &s->nodes[s->n_nodes];
+        orc_node* nd = &s->nodes[self];
         memcpy(nd->bmin, items[0].bmin, sizeof nd->bmin);
         memcpy(nd->bmax, items[0].bmax, sizeof nd->bmax);
         nd->left = nd->right = RTP_MISS;
         nd->leaf = items[0].id;
-        return s->n_nodes++;
+        return self;
     }
     qsort_r(items, n, sizeof *items, item_cmp, &axis);
     size_t half = n / 2; /* bvh.rs:66 split_at_mut(len/2) */
-    uint32_t left = make_bvh(s, items, half, (axis + 1) % 3, depth + 1);
-    uint32_t right = make_bvh(s, items + half, n - half, (axis + 1) % 3, depth + 1);
-    orc_node* nd = &s->nodes[s->n_nodes];
+    const uint32_t left = base + (uint32_t)(2 * half - 2), right = self - 1;
+    if (spawn > 0 && n > 65536) {
+        bvh_job job = {s, items, half, (axis + 1) % 3, depth + 1, base, spawn - 1};
+        pthread_t th;
+        int threaded = pthread_create(&th, NULL, bvh_job_run, &job) == 0;
+        if (!threaded) bvh_job_run(&job);
+        make_bvh_at(s, items + half, n - half, (axis + 1) % 3, depth + 1, left + 1, spawn - 1);
+        if (threaded) pthread_join(th, NULL);
+    } else {
+        make_bvh_at(s, items, half, (axis + 1) % 3, depth + 1, base, 0);
+        make_bvh_at(s, items + half, n - half, (axis + 1) % 3, depth + 1, left + 1, 0);
+    }
+    orc_node* nd = &s->nodes[self];
     const orc_node* l = &s->nodes[left];
     const orc_node* r = &s->nodes[right];
     for (int k = 0; k < 3; ++k) { /* utility.rs:130-135 AABB::union */
@@ -308,7 +332,12 @@ static uint32_t make_bvh(orc_scene* s, orc_item* items, size_t n, int axis, uint
     nd->left = left;
     nd->right = right;
     nd->leaf = RTP_MISS;
-    return s->n_nodes++;
+    return self;
+}
+static uint32_t make_bvh(orc_scene* s, orc_item* items, size_t n, int axis, uint32_t depth) {
+    uint32_t root = make_bvh_at(s, items, n, axis, depth, 0, 5);
+    s->n_nodes = (uint32_t)(2 * n - 1);
+    return root;
 }
 
 /* bvh.rs:70-91 Bvh::new over `n` hittables: boxes, then make_bvh. strict: NaN centroids and Bvh items are errors (the reference panics) */
