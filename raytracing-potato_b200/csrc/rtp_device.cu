@@ -1021,10 +1021,13 @@ struct DRender {
 // path p of a launch = (tile pixel p / n_samples, sample p % n_samples): the samples of one pixel sit in adjacent lanes,
 // so a warp's primary rays are as coherent as they can be
 __device__ __forceinline__ void path_coords(const DRender& rp, size_t p, uint32_t& i, uint32_t& j, uint32_t& smp) {
-    const size_t pix = p / rp.n_samples;
-    smp = rp.sample_begin + static_cast<uint32_t>(p % rp.n_samples);
-    i = rp.tile_x + static_cast<uint32_t>(pix % rp.tile_w);
-    j = rp.tile_y + rp.row_offset + static_cast<uint32_t>(pix / rp.tile_w) * rp.row_stride;
+    // a launch holds at most 32 Mi paths (render_enqueue): 32-bit divisions (the 64-bit ones were 3.6 % of the shade kernel)
+    const uint32_t p32 = static_cast<uint32_t>(p);
+    const uint32_t pix = p32 / rp.n_samples;
+    smp = rp.sample_begin + (p32 - pix * rp.n_samples);
+    const uint32_t row = pix / rp.tile_w;
+    i = rp.tile_x + (pix - row * rp.tile_w);
+    j = rp.tile_y + rp.row_offset + row * rp.row_stride;
 }
 
 // main.rs:70-76: jittered uv (render.rs:76-81), lens sample (render.rs:36, drawn even when lens_radius == 0), Camera::shoot
@@ -1205,8 +1208,11 @@ __device__ __noinline__ void trace_deferred(const DSceneView& sc, D3 o, D3 d, Hi
 
 // GEN0: this is segment 0 of a launch whose primary rays were never written to a queue (trace_any_kernel<.., GEN>): the thread
 // regenerates its path's camera ray (same draws, same bits) instead of reading 80 B of ray and state
+#ifndef RTP_SHADE_BLOCKS
+#define RTP_SHADE_BLOCKS 3
+#endif
 template <bool GEN0>
-__global__ void __launch_bounds__(256, 3) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch, DCamera cam,
+__global__ void __launch_bounds__(256, RTP_SHADE_BLOCKS) wave_shade_kernel(DSceneView sc, DRender rp, WaveQueues wq, uint32_t bounce, double4* __restrict__ scratch, DCamera cam,
                                                             size_t n_gen) {
     const size_t n = GEN0 ? n_gen : static_cast<size_t>(wq.count[bounce]);
     const int cur = bounce & 1, nxt = cur ^ 1;
@@ -2197,7 +2203,7 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         if (e == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
             ds->queue_budget_bytes = std::max<size_t>(size_t(1) << 30, std::min<size_t>(size_t(24) << 30, free_b / 6));
         ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
-        ds->shade_blocks = prop.multiProcessorCount * 3;
+        ds->shade_blocks = prop.multiProcessorCount * RTP_SHADE_BLOCKS;
         if (const char* v = std::getenv("RTP_BUILD_TIMING")) if (std::atoi(v) != 0)
             std::fprintf(stderr, "[rtp build] 4-wide tree depth %u (order-free tree: %u), %s walk (%u big primitives), %zu B of stack per block, %d traversal blocks per SM\n",
                          flat.wide_depth, flat.free_depth, ds->any_order ? (ds->use_combined ? "any-order (combined kernel)" : "any-order") : "in-order", flat.n_big,
@@ -2530,7 +2536,7 @@ static int render_enqueue(DeviceScene* ds, const rtp_camera* camera, const rtp_r
     const bool wave = !ds->use_simple_render;
     const size_t per_path = wave ? 176 + 48 * static_cast<size_t>(p->max_bounce) + 32 : 32;
     size_t path_budget = std::max<size_t>(size_t(1) << 20, std::min<size_t>(size_t(32) << 20, ds->queue_budget_bytes / per_path));
-    if (const char* v = std::getenv("RTP_PATH_BUDGET")) path_budget = std::max<size_t>(1, static_cast<size_t>(std::atoll(v)));  // tests: force several launches per frame
+    if (const char* v = std::getenv("RTP_PATH_BUDGET")) path_budget = std::min<size_t>(size_t(1) << 31, std::max<size_t>(1, static_cast<size_t>(std::atoll(v))));  // tests: force several launches per frame
     uint32_t per_launch = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(ns_total ? ns_total : 1, path_budget / npix)));
     const size_t need = npix * per_launch;
     if (wave && ns_total) {
