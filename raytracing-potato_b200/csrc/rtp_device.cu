@@ -62,6 +62,9 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterp
 
 struct Counters {
     unsigned long long rays, paths, node_visits, triangle_tests, sphere_tests, leaf_gates, violations, rewalks;
+    // lane occupancy of trace_any_kernel's rounds (counting builds, RTP_LANE_STATS=1 prints them): per round, how many lanes could
+    // walk, sat on two pending leaves, had a leaf pending but nothing left to walk, or held no ray
+    unsigned long long rounds, lanes_walk, lanes_full, lanes_leafwait, lanes_empty, leaf_rounds, leaf_lanes, step_lanes;
 };
 
 struct LocalCounters {
@@ -1593,6 +1596,12 @@ __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D
 #ifndef RTP_ANY_STEPS
 #define RTP_ANY_STEPS 2   // walk steps per round of votes
 #endif
+#ifndef RTP_ANY_POPLOOP
+#define RTP_ANY_POPLOOP 1 // 1: a step pops until it has a node to visit (0: one stack entry per step)
+#endif
+#ifndef RTP_ANY_PICK
+#define RTP_ANY_PICK 1    // 1: a round tests leaves first when more lanes wait for a leaf test than can walk
+#endif
 // GEN (wavefront integrator, segment 0): ray i IS camera path i of the launch (main.rs:70-76: jitter, lens draw, Camera::shoot), made
 // here from (camera, frame parameters) instead of being read from a queue a generate kernel wrote: saves an 80 B/path round trip
 // through HBM and one launch per frame; wave_shade_kernel<GEN0> regenerates the same ray when it shades the vertex.
@@ -1759,11 +1768,35 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
             }
         }
 
+        if (COUNT) {
+            const bool cw = (leaf1 == 0u) & ((node != kNone) | (sp != sbase));
+            const unsigned m_walk = __ballot_sync(0xffffffffu, cw), m_full = __ballot_sync(0xffffffffu, leaf1 != 0u);
+            const unsigned m_wait = __ballot_sync(0xffffffffu, !cw & (leaf0 != 0u) & (leaf1 == 0u));
+            const unsigned m_empty = __ballot_sync(0xffffffffu, !cw & (leaf0 == 0u));
+            if (lane == 0 && counters) {
+                atomicAdd(&counters->rounds, 1ull); atomicAdd(&counters->lanes_walk, static_cast<unsigned long long>(__popc(m_walk)));
+                atomicAdd(&counters->lanes_full, static_cast<unsigned long long>(__popc(m_full))); atomicAdd(&counters->lanes_leafwait, static_cast<unsigned long long>(__popc(m_wait)));
+                atomicAdd(&counters->lanes_empty, static_cast<unsigned long long>(__popc(m_empty)));
+            }
+        }
+        // ---- which phase: when more lanes wait for a leaf test than can walk, test leaves first (incoherent rays: a few long walks
+        //      would otherwise run at a handful of lanes while most of the warp waits for its primitive tests) ---------------------
+        bool leaf_first = false;
+#if RTP_ANY_PICK
+        {
+            const int n_walk = __popc(__ballot_sync(0xffffffffu, (leaf1 == 0u) & ((node != kNone) | (sp != sbase))));
+            const int n_leaf = __popc(__ballot_sync(0xffffffffu, leaf0 != 0u));
+            leaf_first = n_leaf >= tune.prim_batch && n_leaf > n_walk;
+        }
+#endif
         // ---- walk: up to two steps per round ----------------------------------------------------------------------------------
+        if (!leaf_first) {
 #pragma unroll
         for (int rep = 0; rep < RTP_ANY_STEPS; ++rep) {
             if ((leaf1 == 0u) & ((node != kNone) | (sp != sbase))) {
-                if (node == kNone) {
+                // take postponed entries until one gives a node to visit: leaves go to the pending pair, entries beyond the window are
+                // dropped. (One entry per step left half of the step slots of incoherent rays without a node: RTP_LANE_STATS.)
+                while ((node == kNone) & (sp != sbase) & (leaf1 == 0u)) {
                     sp -= kAnyStride;
                     const uint2 e = lds_v2(sp);
                     if (__uint_as_float(e.y) <= T_up) {  // else: the window shrank since this entry was postponed
@@ -1773,6 +1806,9 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                             node = e.x;
                         }
                     }
+#if !RTP_ANY_POPLOOP
+                    break;
+#endif
                 }
                 if (node != kNone) {
                     const uint32_t nb = node * 8u;
@@ -1830,12 +1866,14 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                 }
             }
         }
+        }
 
         // ---- leaves: when enough lanes hold one, or nobody can walk ----------------------------------------------------------
         const unsigned parked = __ballot_sync(0xffffffffu, leaf0 != 0u);
         if (parked != 0u) {
             const unsigned walking = __ballot_sync(0xffffffffu, (leaf1 == 0u) & ((node != kNone) | (sp != sbase)));
             if (__popc(parked) >= tune.prim_batch || walking == 0u) {
+                if (COUNT && lane == 0 && counters) { atomicAdd(&counters->leaf_rounds, 1ull); atomicAdd(&counters->leaf_lanes, static_cast<unsigned long long>(__popc(parked))); }
                 if (leaf0 != 0u) {
                     if (!(leaf0 & kWideBig)) test_leaf(leaf0);  // big primitives were tested when the ray started
                     leaf0 = leaf1;
@@ -2977,6 +3015,10 @@ int rtp_trace_closest_device_counted(rtp_scene* scene, const rtp_ray* d_rays, si
     RTP_CUDA(cudaMemcpy(&c, ds->counters, sizeof c, cudaMemcpyDeviceToHost));
     float ms = 0.f;
     RTP_CUDA(cudaEventElapsedTime(&ms, ds->ev_begin, ds->ev_end));
+    if (std::getenv("RTP_LANE_STATS") && c.rounds)
+        std::fprintf(stderr, "[rtp lanes] %llu rounds (%.1f per ray): per round %.1f lanes can walk, %.1f hold two leaves, %.1f wait for a leaf test with nothing left to walk, %.1f hold no ray; "
+                             "%llu leaf rounds at %.1f lanes\n", c.rounds, double(c.rounds) * 32.0 / double(c.rays ? c.rays : 1), double(c.lanes_walk) / c.rounds, double(c.lanes_full) / c.rounds,
+                     double(c.lanes_leafwait) / c.rounds, double(c.lanes_empty) / c.rounds, c.leaf_rounds, c.leaf_rounds ? double(c.leaf_lanes) / c.leaf_rounds : 0.0);
     std::memset(stats, 0, sizeof *stats);
     stats->rays = c.rays; stats->node_visits = c.node_visits; stats->triangle_tests = c.triangle_tests; stats->sphere_tests = c.sphere_tests; stats->leaf_gates = c.leaf_gates; stats->conservative_violations = c.violations; stats->order_rewalks = c.rewalks;
     stats->device_ms = ms; stats->kernel_launches = 1;
