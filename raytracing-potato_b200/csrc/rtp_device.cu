@@ -472,12 +472,6 @@ struct Walker {
     bool m32;        // eligible for the f32 culling walk
     bool need_gate;  // parked by the f32 walk: the leaf's exact f64 gate has not been evaluated yet
     bool sx, sy, sz;
-    // any-order walk (walker_step_any): `any` = this lane is in that mode; T_win = the window top min(ray.t_max, t_best +
-    // 2 slack(t_best)) that culls boxes and bounds the primitive tests; A_min = smallest t of a tested leaf that passes its
-    // static tests but whose own box entry lies above its t (its acceptance depends on the reference's visiting order)
-    bool any;
-    double T_win, A_min;
-    float s0f, s1f;  // slack(t) = s0f + s1f |t|, rounded up
 };
 
 // utility.rs:71-77 Ray::expand plus the derived quantities of the fast paths
@@ -505,7 +499,6 @@ __device__ __forceinline__ void walker_start(Walker& w, const DSceneView& sc, co
     w.pend = 0; w.sp = 0; w.cur = 0;
     w.prim = kNoPrim; w.prim2 = kNoPrim;
     w.need_gate = false;
-    w.any = false;
 }
 
 // One step of an f32-eligible lane that is walking (next != kEnd, not parked): visit `next` if there is one (four
@@ -561,7 +554,7 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
 }
 
 // ---------------------------------------------------------------------------------------------
-// Any-order walk. The reference's result is that of the sequential process
+// Any-order walk: trace_any_kernel, further down. The reference's result is that of the sequential process
 //     T = ray.t_max; for leaf p in DFS order: if T >= m_p: T = t_p, best = p
 // where, for a leaf that passes its static tests (box entered at all, barycentrics inside, t_p >= t_min), t_p is the computed
 // hit distance and m_p = max(t_p, computed slab entry of p's own box) — both independent of T. A leaf is NORMAL when
@@ -570,164 +563,10 @@ __device__ __forceinline__ void walker_step_wide(Walker& w, const DSceneView& sc
 // looked at. slack(t) bounds m_p - t_p for every primitive that is not "big" (error analysis of hittable.rs:39-57, 77-95 in
 // DESIGN.md §4b), so a box whose conservative entry lies above T_win = t_best + 2 slack(t_best) holds no leaf that can matter and
 // is skipped, children are visited nearest first, and the primitive tests use T_win as their upper bound. Big primitives (the
-// outsized ones of a scene, at most eight) are exempt from the window: a child that is or contains one is tested against the
-// ray's own t_max, visited first and never dropped. A ray that met an abnormal leaf inside the final window is
-// walked again in the reference's order (walker_step_wide): exactness never rests on the bound being tight, only on it
-// being a bound.
+// outsized ones of a scene, at most eight) are tested for every ray before its walk starts. A ray that met an abnormal leaf inside
+// the final window is traced again in the reference's order by the kernel below (its index mode): exactness never rests on the
+// bound being tight, only on it being a bound.
 // ---------------------------------------------------------------------------------------------
-
-// per-ray slack coefficients; false: the ray is not eligible (bounds not self-consistent, or not finite)
-__device__ __forceinline__ bool any_slack(const Walker& w, const DSceneView& sc, float& s0f, float& s1f) {
-    // evaluated in f32 with every operation rounded up (all quantities are non-negative), so the result is an upper bound of
-    // the real-number expression in DESIGN.md 4b; an overflow to +inf makes the ray ineligible
-    const float u = 0x1.0p-53f, K = 8.9e-9f;  // K >= 8 u 1e7: |det| >= 1e-7 (hittable.rs:80), 8u: rounding of a 6-term sum of products
-    const float P = __fadd_ru(__double2float_ru(fmax(fmax(fabs(w.o.x), fabs(w.o.y)), fabs(w.o.z))), sc.any_Af);
-    const float D = __double2float_ru(fmax(fmax(fabs(w.d.x), fabs(w.d.y)), fabs(w.d.z)));
-    const float I = __double2float_ru(fmax(fmax(fabs(w.inv.x), fabs(w.inv.y)), fabs(w.inv.z)));
-    const float E = sc.any_Ef;
-    const float E2 = __fmul_ru(E, E), DE2 = __fmul_ru(D, E2), PE = __fmul_ru(P, E);
-    const float kappa = __fmul_ru(__fmul_ru(K, 6.0f), DE2);
-    const float e_uv = __fadd_ru(__fmul_ru(K, __fadd_ru(__fmul_ru(6.0f, __fmul_ru(PE, D)), __fmul_ru(6.06f, DE2))), 3.0f * u);
-    if (!(kappa <= 0.25f) || !(e_uv <= 0.01f)) return false;
-    const float eta = __fmul_ru(__fadd_ru(__fmul_ru(4.0f, e_uv), 5.0f * u), E);
-    // 1 / (1 - kappa) <= 4/3 for kappa <= 1/4: no divide on the per-ray path; the factor 4 in front absorbs the second-order terms
-    const float a0 = __fmul_ru(__fmul_ru(__fadd_ru(eta, __fmul_ru(u, P)), I), 1.0000002f);
-    const float a1 = __fmul_ru(__fmul_ru(__fmul_ru(K, 6.0f), __fmul_ru(PE, E)), 1.3333334f);
-    const float a2 = __fmul_ru(3.0f * u, __double2float_ru(fabs(w.tmin)));
-    float a3 = 0.f;
-    if (sc.any_Rf >= 0.f) {
-        // spheres that are not big (hittable.rs:39-57): delta = half_b^2 - a (|o-c|^2 - r^2) carries an absolute error of at most
-        // 40 u |d|^2 S with S = |o-c|^2 + r^2, a root sqrt(40 u S) / |d|; a grazing ray adds the same once for the root gap and
-        // once for the closest point lying that far outside the sphere (times |1/d| on the slab axis): 3 sqrt(40 u S) |1/d|max
-        const float Po = __double2float_ru(fmax(fmax(fabs(w.o.x), fabs(w.o.y)), fabs(w.o.z)));
-        const float oc = __fadd_ru(Po, sc.any_Cf);
-        const float S = __fadd_ru(__fmul_ru(3.0f, __fmul_ru(oc, oc)), __fmul_ru(sc.any_Rf, sc.any_Rf));
-        const float g = __fsqrt_ru(__fmul_ru(40.0f * u, S));
-        a3 = __fmul_ru(__fadd_ru(__fmul_ru(3.0f, g), __fmul_ru(u, __fadd_ru(__fmul_ru(2.0f, __fadd_ru(sc.any_Cf, sc.any_Rf)), oc))), I);
-    }
-    s0f = __fmul_ru(4.0f, __fadd_ru(__fadd_ru(__fadd_ru(a0, a1), a2), a3));
-    s1f = __fmul_ru(4.0f, __fadd_ru(__fmul_ru(__fadd_ru(__fmul_ru(__fmul_ru(K, 6.0f), DE2), 5.0f * u), 1.3333334f), 8.0f * u));
-    return s0f <= 3.0e38f && s1f <= 3.0e38f;
-}
-
-// exact test of one leaf in any-order mode: static tests with the window top as the upper bound, then classification
-template <bool COUNT>
-__device__ __forceinline__ void any_test(Walker& w, const DSceneView& sc, LocalCounters& lc, uint32_t prim) {
-    const uint32_t slot = prim & 0x7FFFFFFFu, kind = prim >> 31;
-    const DPrim* p = sc.prims + slot;
-    double t, u = 0.0, v = 0.0;
-    bool hit;
-    if (kind == RTP_HITTABLE_TRIANGLE) {
-        if (COUNT) lc.triangle_tests++;
-        hit = test_triangle(p, w.o, w.d, w.tmin, w.T_win, t, u, v);
-    } else {
-        if (COUNT) lc.sphere_tests++;
-        hit = test_sphere(p, w.o, w.d, w.tmin, w.T_win, t);
-    }
-    if (!hit) return;
-    if (!(t == t)) { w.A_min = -CUDART_INF; return; }  // NaN t (overflowing geometry): let the in-order walk decide
-    const double* pb = p->bmin;
-    const double2 b0 = ldg2(pb), b1 = ldg2(pb + 2), b2 = ldg2(pb + 4);
-    if (COUNT) lc.leaf_gates++;
-    if (collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, t)) {
-        // normal leaf: min t, ties to the larger DFS rank (= slot)
-        if (w.h.slot == kNoPrim || t < w.h.t || (t == w.h.t && slot > w.h.slot)) {
-            w.h.t = t; w.h.u = u; w.h.v = v; w.h.slot = slot; w.h.kind = kind;
-            const double win = t + 2.0 * (static_cast<double>(w.s0f) + static_cast<double>(w.s1f) * fabs(t));
-            w.T_win = fmin(w.T_win, win);
-            w.r32.T_up = __double2float_ru(w.T_win);
-        }
-    } else if (collide_fast(b0, b1, b2, w.o, w.inv, w.sx, w.sy, w.sz, w.tmin, CUDART_INF)) {
-        w.A_min = fmin(w.A_min, t);  // abnormal: its box is entered, but only after t
-    }
-}
-
-// switch a freshly started lane (walker_start) to any-order mode if scene and ray allow it, and test the big primitives
-template <bool COUNT>
-__device__ __forceinline__ void any_begin(Walker& w, const DSceneView& sc, LocalCounters& lc) {
-    w.any = false;
-    if (!(sc.any_order != 0u && w.m32 && w.tmin >= 0.0)) return;
-    if (!any_slack(w, sc, w.s0f, w.s1f)) return;
-    w.any = true;
-    w.T_win = w.h.t;
-    w.A_min = CUDART_INF;
-}
-
-// hand a child word to the lane: a leaf is parked (oldest pending leaf first), an internal child becomes the node to visit; selects only
-__device__ __forceinline__ void any_take(Walker& w, uint32_t c) {
-    const bool is_leaf = (c & kWideLeaf) != 0u;
-    const uint32_t leaf = ((c >> 30) & 1u) << 31 | (c & kWideSlotMask);
-    const bool first = w.prim == kNoPrim;
-    w.prim2 = (is_leaf & !first) ? leaf : w.prim2;
-    w.prim = (is_leaf & first) ? leaf : w.prim;
-    w.next = is_leaf ? kNone : c;
-}
-
-// One step of a lane in any-order mode: take a node (the pending one, else the nearest postponed entry that survives the
-// window), test its four children, postpone the farther ones with their entry distance, go on with the nearest. `stack` is
-// this thread's column of (child word, entry distance) pairs.
-template <bool COUNT>
-__device__ __forceinline__ void walker_step_any(Walker& w, const DSceneView& sc, LocalCounters& lc, uint2* __restrict__ stack, uint32_t stride) {
-    if (w.next == kNone) {
-        if (w.sp == 0u) { w.next = kEnd; return; }
-        w.sp -= 1u;
-        const uint2 e = stack[w.sp * stride];
-        if (__uint_as_float(e.y) > w.r32.T_up) return;  // the window shrank since this entry was postponed
-        any_take(w, e.x);
-        if (w.next == kNone) return;
-    }
-    const char* np = reinterpret_cast<const char*>(sc.any_wide + w.next);
-    const float4 nx4 = __ldg(reinterpret_cast<const float4*>(np + w.onx));
-    const float4 fx4 = __ldg(reinterpret_cast<const float4*>(np + (16u - w.onx)));
-    const float4 ny4 = __ldg(reinterpret_cast<const float4*>(np + 32u + w.ony));
-    const float4 fy4 = __ldg(reinterpret_cast<const float4*>(np + 32u + (16u - w.ony)));
-    const float4 nz4 = __ldg(reinterpret_cast<const float4*>(np + 64u + w.onz));
-    const float4 fz4 = __ldg(reinterpret_cast<const float4*>(np + 64u + (16u - w.onz)));
-    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 96u));
-    const uint32_t big = __ldg(reinterpret_cast<const uint32_t*>(np + 112u));
-    const Ray32& r = w.r32;
-    // key = entry distance (non-negative float: its bits order like the value) with the child index in the two low bits;
-    // children that are missed, beyond the window or empty get the largest key. A child that holds a big primitive (big_mask)
-    // is exempt from the window - the slack bound does not cover what is inside - and gets key 0: visited first, never
-    // dropped when it is popped, so a big primitive is tested whenever the ray enters its box at all
-#define RTP_KEY(c, idx)                                                                                                        \
-    const bool g##c = ((big >> idx) & 1u) != 0u;                                                                                   \
-    const float n##c = fmaxf(fmaxf(fmaf(nx4.c, r.ix, r.clx), fmaf(ny4.c, r.iy, r.cly)), fmaxf(fmaf(nz4.c, r.iz, r.clz), r.tmin_dn)); \
-    const float f##c = fminf(fminf(fmaf(fx4.c, r.ix, r.chx), fmaf(fy4.c, r.iy, r.chy)), fminf(fmaf(fz4.c, r.iz, r.chz), g##c ? CUDART_INF_F : r.T_up)); \
-    const uint32_t k##c = f##c >= n##c ? ((g##c ? 0u : (__float_as_uint(n##c) & ~3u)) | idx) : 0xFFFFFFFFu;
-    RTP_KEY(x, 0u) RTP_KEY(y, 1u) RTP_KEY(z, 2u) RTP_KEY(w, 3u)
-#undef RTP_KEY
-    if (COUNT) {
-        lc.node_visits++;
-        const double* b64 = sc.any_boxes + static_cast<size_t>(w.next) * 24;
-        const uint32_t keys[4] = {kx, ky, kz, kw};
-        for (uint32_t k = 0; k < 4; ++k)  // a rejected child must fail the exact test with the window top as t_max
-            if (keys[k] == 0xFFFFFFFFu && (&ch.x)[k] != kWideEmpty &&
-                collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), w.o, w.inv, w.tmin, ((big >> k) & 1u) ? CUDART_INF : w.T_win))
-                lc.violations++;
-    }
-    // sorting network for four keys (measured: visiting the postponed children nearest-first beats index order everywhere)
-    const uint32_t a0 = min(kx, ky), a1 = max(kx, ky), b0 = min(kz, kw), b1 = max(kz, kw);
-    const uint32_t s0 = min(a0, b0), m0 = max(a0, b0), m1 = min(a1, b1), s3 = max(a1, b1);
-    const uint32_t s1 = min(m0, m1), s2 = max(m0, m1);
-    if (w.sp + 3u > sc.any_cap) {
-        // no room to postpone three children (the stack holds any_cap entries per lane): give the ray to the in-order walk
-        w.next = kEnd; w.prim = kNoPrim; w.prim2 = kNoPrim; w.A_min = -CUDART_INF;
-        return;
-    }
-#define RTP_SEL(k) __funnelshift_rc(__funnelshift_rc(ch.x, ch.y, ((k) & 1u) << 5), __funnelshift_rc(ch.z, ch.w, ((k) & 1u) << 5), ((k) & 2u) << 4)
-    // (an L2 prefetch of the postponed child's record was measured 3 % slower on the bunny and on the C5 scene alike)
-#define RTP_PUSH(s)                                                                       \
-    if ((s) != 0xFFFFFFFFu) {                                                             \
-        stack[w.sp * stride] = make_uint2(RTP_SEL(s), (s) & ~3u);                         \
-        w.sp += 1u;                                                                       \
-    }
-    RTP_PUSH(s3) RTP_PUSH(s2) RTP_PUSH(s1)
-#undef RTP_PUSH
-    w.next = kNone;
-    if (s0 != 0xFFFFFFFFu) any_take(w, RTP_SEL(s0));
-#undef RTP_SEL
-}
 
 // One exact f64 step for lanes outside the f32 path's preconditions (bvh.rs:93-119 literally, or collide_fast).
 template <bool COUNT>
@@ -1327,13 +1166,14 @@ struct TailArgs {
 
 constexpr int kTraceBlocksPerSM = 6;
 
-// ANY: 0 = every lane walks in the reference's order; 1, 2 = eligible lanes take the any-order walk, built for 5 resident blocks per
-// SM (96 registers, a few spills: best while the scene is cache-resident) or 4 (120 registers, none: best for scenes in HBM)
-template <bool COUNT, int OUT, bool LIST, int ANY>
-__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (ANY == 1 ? 5 : kTraceBlocksPerSM))) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
+// The in-order kernel: every lane walks in the reference's order (f32-eligible lanes on the 4-wide tree, the others on the exact f64
+// pre-order tree). It serves List roots, scenes outside the any-order walk's preconditions, tail-mode launches, and the rays
+// trace_any_kernel defers (index mode).
+template <bool COUNT, int OUT, bool LIST>
+__global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) trace_persistent_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out,
                                                                   Counters* counters, WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev,
                                                                   TailArgs ta, DeferList index) {
-    extern __shared__ __align__(16) uint32_t wide_stack[];  // [level][thread]; any-order lanes: [entry][thread] of uint2
+    extern __shared__ __align__(16) uint32_t wide_stack[];  // [level][thread]
     if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
     if (index.idx) n = static_cast<size_t>(*index.count);  // index mode: trace rays[index.idx[q]] for q < *index.count (deferred by trace_any_kernel)
     if (OUT == OUT_TAIL) {
@@ -1343,10 +1183,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
     uint4 pst = make_uint4(0, 0, 0, 0);  // tail mode: the path state of the lane's ray (WaveQueues::state)
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // any-order kernels: every thread owns a column of uint2 entries; a lane walking in the reference's order (re-walk) keeps
-    // its one-word entries in the .x halves of its own column, so lanes in different modes never touch each other's stack
-    uint32_t* const my_stack = wide_stack + (ANY ? 2u : 1u) * threadIdx.x;
-    uint2* const my_stack2 = reinterpret_cast<uint2*>(wide_stack) + threadIdx.x;
+    uint32_t* const my_stack = wide_stack + threadIdx.x;
     const uint32_t stride = blockDim.x;
     constexpr size_t kNoRay = ~static_cast<size_t>(0);
     LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
@@ -1358,7 +1195,6 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
     w.tmin = 0.0; w.h.t = 0.0; w.h.u = w.h.v = 0.0; w.h.slot = kNoPrim; w.h.kind = 0;
     w.next = kEnd; w.prim = kNoPrim; w.prim2 = kNoPrim; w.cur = 0; w.pend = 0; w.sp = 0; w.c0 = w.c1 = w.c2 = w.c3 = 0; w.onx = w.ony = w.onz = 0;
     w.fast = true; w.m32 = true; w.need_gate = false; w.sx = w.sy = w.sz = false;
-    w.any = false; w.T_win = 0.0; w.A_min = 0.0; w.s0f = w.s1f = 0.f;
     w.r32 = Ray32{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     size_t idx = kNoRay;
     bool more = true;  // warp-uniform: the queue may still hold rays
@@ -1367,18 +1203,6 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
     const int refill_thr = min(tune.refill_min, max(1, lane_cap / 2));
 
     for (;;) {
-        if (ANY) {
-            // an any-order lane whose walk is over: if an abnormal leaf lies inside the final window, the answer may depend on the
-            // reference's visiting order, so the ray is walked again in that order (walker_step_wide)
-            if ((w.next == kEnd) & (w.prim == kNoPrim) & w.any) {
-                w.any = false;
-                if (w.A_min <= w.T_win && w.A_min != CUDART_INF) {
-                    const double t0 = OUT == OUT_TAIL ? CUDART_INF : __ldg(&rays[idx].t_max);
-                    walker_start(w, sc, tune, w.o, w.d, w.tmin, t0);
-                    if (COUNT) lc.rewalks++;
-                }
-            }
-        }
         // ---- retire finished rays and refill ----------------------------------------------------------
         const bool is_done = (w.next == kEnd) & (w.prim == kNoPrim);
         const bool fin = OUT == OUT_TAIL && is_done && idx != kNoRay;  // tail mode: walk over, vertex not shaded yet
@@ -1421,7 +1245,6 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
                     if (alive) {
                         walker_start(w, sc, tune, o, d, kRayEpsilon, CUDART_INF);
                         if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
-                        if (ANY && !LIST) any_begin<COUNT>(w, sc, lc);
                         lc.rays++;
                     } else {
                         for (int b = static_cast<int>(nb) - 1; b >= 0; --b) {
@@ -1459,7 +1282,6 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
                     const double2 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
                     walker_start(w, sc, tune, mk(r0.x, r0.y, r1.x), mk(r1.y, r2.x, r2.y), r3.x, r3.y);
                     if (LIST) { w.m32 = false; if (sc.n_prims == 0) w.next = kEnd; }
-                    if (ANY && !LIST) any_begin<COUNT>(w, sc, lc);
                     if (OUT == OUT_TAIL) pst = ta.q.state[ta.bounce & 1u][i];
                     lc.rays++;
                 }
@@ -1486,10 +1308,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
             for (;;) {
 #pragma unroll
                 for (int rep = 0; rep < 2; ++rep)  // measured: 3 or 4 steps per vote are slower in both walks
-                    if ((w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32) {
-                        if (ANY && w.any) walker_step_any<COUNT>(w, sc, lc, my_stack2, stride);
-                        else walker_step_wide<COUNT>(w, sc, lc, my_stack, ANY ? 2u * stride : stride);
-                    }
+                    if ((w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32) walker_step_wide<COUNT>(w, sc, lc, my_stack, stride);
                 const unsigned walking = __ballot_sync(0xffffffffu, (w.next != kEnd) & (w.prim2 == kNoPrim) & w.m32);
                 if (walking == 0u) break;
                 const unsigned parked = __ballot_sync(0xffffffffu, w.prim != kNoPrim);
@@ -1503,15 +1322,7 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : (ANY == 2 ? 4 : (AN
         }
 
         // ---- leaves: exact gate + primitive test for the parked lanes --------------------------------
-        if (w.prim != kNoPrim) {
-            if (ANY && w.any) {
-                any_test<COUNT>(w, sc, lc, w.prim);
-                w.prim = w.prim2;
-                w.prim2 = kNoPrim;
-            } else {
-                walker_leaf<COUNT>(w, sc, lc);
-            }
-        }
+        if (w.prim != kNoPrim) walker_leaf<COUNT>(w, sc, lc);
     }
 
     flush_counters<COUNT>(counters, lc);
@@ -2026,13 +1837,11 @@ struct DeviceScene {
     std::mutex launch_lock;            // acquire slot + enqueue + record event is one critical section per launch
     unsigned slot_seq = 0;
     WorkQueue* queues = nullptr;       // backing store of the slots' queues and defer counters
-    int persistent_blocks = 0;         // grid of the in-order persistent kernel: SM count x resident blocks per SM
-    int inorder_blocks = 0, inorder_tail_blocks = 0;  // grids of the ANY = 0 build (persistent_blocks / tail_blocks are the combined kernel's when that is in use)
+    int inorder_blocks = 0, inorder_tail_blocks = 0;  // grids of the in-order kernel (batch / tail mode)
     size_t inorder_stack_bytes = 0;
     int any_blocks = 0;                // grid of trace_any_kernel
     size_t any_stack_bytes = 0;        // its dynamic shared memory: any_cap x 128 threads x 8 B
-    bool use_combined = false;         // RTP_TRACE_KERNEL=combined: the round-1 kernel with both walkers compiled in (A/B runs)
-    int any_order = 0;                 // 1, 2: eligible rays take the any-order walk (RTP_TRAVERSAL), kernel variant ANY = 1 or 2
+    int any_order = 0;                 // != 0: eligible rays take the any-order walk (RTP_TRAVERSAL); 2 marks a scene of >= 262,144 leaves
     uint32_t any_cap = 0;              // any-order stack entries per lane
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
     Tuning tune{16, 4, 1, 1, 2, 1};           // RTP_REFILL_MIN / RTP_PRIM_BATCH / RTP_FAST_SLAB override (tuning runs only)
@@ -2052,7 +1861,6 @@ struct DeviceScene {
     WaveQueues wave{};                 // wavefront integrator queues (render_device), grown on demand
     uint32_t wave_bounces = 0;         // stack depth the queues were sized for
     int shade_blocks = 0;              // grid of wave_shade_kernel
-    int tail_blocks = 0;               // grid of the tail-mode traversal kernel
     uint32_t tail_threshold = 65536;   // RTP_TAIL_THRESHOLD: a launch this small is finished by one tail-mode launch (0 = never)
     bool tail_offer = false;           // RTP_TAIL_OFFER
     size_t queue_budget_bytes = size_t(4) << 30;  // memory the integrator's per-launch buffers may take (set at upload from the free HBM)
@@ -2171,7 +1979,6 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         if (const char* v = std::getenv("RTP_F32_CULLING")) if (std::atoi(v) == 0) want = false;
         // scenes that live in HBM rather than in the caches run the spill-free 4-blocks-per-SM build of the kernel
         ds->any_order = (want && flat.any_ok && f32_ok) ? (flat.prim_count() >= kAnyOrderBigScene ? 2 : 1) : 0;
-        if (const char* v = std::getenv("RTP_ANY_VARIANT")) if (ds->any_order) ds->any_order = std::atoi(v) == 2 ? 2 : 1;
     }
     if (flat.dev.valid) {
         if ((rc = take(&ds->prims, flat.dev.prims, flat.dev.n_prims)) != RTP_OK) return bail(rc);
@@ -2205,13 +2012,11 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         cudaDeviceProp prop;
         e = cudaGetDeviceProperties(&prop, ds->device);
         int per_sm = 0, tail_per_sm = 0, any_per_sm = 0;
-        const char* env_k = std::getenv("RTP_TRACE_KERNEL");
-        ds->use_combined = env_k && std::string(env_k) == "combined";
         // in-order kernel (every scene: List roots, scenes outside the any-order walk's preconditions, the rays trace_any_kernel
         // defers, tail-mode launches): one stack word per tree level and thread
         ds->inorder_stack_bytes = ds->stack_bytes;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 0>, 128, ds->inorder_stack_bytes);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 0>, 128, ds->inorder_stack_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false>, 128, ds->inorder_stack_bytes);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false>, 128, ds->inorder_stack_bytes);
         ds->inorder_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->inorder_tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (ds->any_order) {
@@ -2224,29 +2029,15 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
             ds->any_stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&any_per_sm, trace_any_kernel<false, OUT_HIT, false>, 128, ds->any_stack_bytes);
             ds->any_blocks = prop.multiProcessorCount * std::max(any_per_sm, 1);
-            if (ds->use_combined) {
-                // the round-1 kernel: in-order entries live in the .x halves of the same uint2 columns, at least `depth` of them
-                ds->any_cap = std::max<uint32_t>(flat.wide_depth, ds->any_cap);
-                ds->stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
-                if (ds->any_order == 2) {
-                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 2>, 128, ds->stack_bytes);
-                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 2>, 128, ds->stack_bytes);
-                } else {
-                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_persistent_kernel<false, OUT_HIT, false, 1>, 128, ds->stack_bytes);
-                    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tail_per_sm, trace_persistent_kernel<false, OUT_TAIL, false, 1>, 128, ds->stack_bytes);
-                }
-            }
         }
         size_t free_b = 0, total_b = 0;
         if (e == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
             ds->queue_budget_bytes = std::max<size_t>(size_t(1) << 30, std::min<size_t>(size_t(24) << 30, free_b / 6));
-        ds->persistent_blocks = prop.multiProcessorCount * std::max(per_sm, 1);
         ds->shade_blocks = prop.multiProcessorCount * RTP_SHADE_BLOCKS;
         if (const char* v = std::getenv("RTP_BUILD_TIMING")) if (std::atoi(v) != 0)
             std::fprintf(stderr, "[rtp build] 4-wide tree depth %u (order-free tree: %u), %s walk (%u big primitives), %zu B of stack per block, %d traversal blocks per SM\n",
-                         flat.wide_depth, flat.free_depth, ds->any_order ? (ds->use_combined ? "any-order (combined kernel)" : "any-order") : "in-order", flat.n_big,
-                         ds->any_order && !ds->use_combined ? ds->any_stack_bytes : ds->stack_bytes, ds->any_order && !ds->use_combined ? any_per_sm : per_sm);
-        ds->tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
+                         flat.wide_depth, flat.free_depth, ds->any_order ? "any-order" : "in-order", flat.n_big,
+                         ds->any_order ? ds->any_stack_bytes : ds->stack_bytes, ds->any_order ? any_per_sm : per_sm);
         if (const char* v = std::getenv("RTP_TAIL_THRESHOLD")) ds->tail_threshold = static_cast<uint32_t>(std::max(0l, std::atol(v)));
         if (const char* v = std::getenv("RTP_TAIL_OFFER")) ds->tail_offer = std::atoi(v) != 0;
         const char* env = std::getenv("RTP_TRACE_KERNEL");
@@ -2334,10 +2125,9 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
         const size_t want = (n + 3) / 4;  // a warp per ray at least: small batches are latency-bound per warp, so they are spread thin
         const bool list = ds->view.root_kind != RTP_ROOT_BVH;
         const TailArgs ta = tail ? *tail : TailArgs{};
-        // which build: the pure any-order kernel + a deferred in-order launch (default for eligible scenes), the in-order kernel
-        // alone (List roots, scenes outside the preconditions, tail-mode launches), or round 1's combined kernel (A/B runs)
-        const bool pure_any = !list && ds->any_order && !ds->use_combined && out_mode != OUT_TAIL;
-        const int any = (list || !ds->use_combined) ? 0 : ds->any_order;
+        // which kernel: the any-order kernel + a deferred in-order launch (eligible scenes), or the in-order kernel alone (List roots,
+        // scenes outside the preconditions, tail-mode launches)
+        const bool pure_any = !list && ds->any_order && out_mode != OUT_TAIL;
         if (n > 0xFFFFFFFEull && pure_any) return set_error(RTP_ERR_INVALID, "ray batch too large for one launch");
 
         std::lock_guard<std::mutex> guard(ds->launch_lock);
@@ -2383,23 +2173,21 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
             }
             // the deferred rays (normally none: the launch then finds an empty list and leaves at once), in the reference's order
             const dim3 g2(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->inorder_blocks), want)));
-#define RTP_LAUNCH_DEFERRED(C, O) trace_persistent_kernel<C, O, false, 0><<<g2, block, ds->inorder_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, nullptr, ta, defer)
+#define RTP_LAUNCH_DEFERRED(C, O) trace_persistent_kernel<C, O, false><<<g2, block, ds->inorder_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, nullptr, ta, defer)
             if (out_mode == OUT_FULL) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_FULL); else RTP_LAUNCH_DEFERRED(false, OUT_FULL); }
             else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_WAVE); else RTP_LAUNCH_DEFERRED(false, OUT_WAVE); }
             else { if (count) RTP_LAUNCH_DEFERRED(true, OUT_HIT); else RTP_LAUNCH_DEFERRED(false, OUT_HIT); }
 #undef RTP_LAUNCH_DEFERRED
             ds->last_trace_launches = 2;
         } else {
-            const int blocks = any ? (out_mode == OUT_TAIL ? ds->tail_blocks : ds->persistent_blocks) : (out_mode == OUT_TAIL ? ds->inorder_tail_blocks : ds->inorder_blocks);
-            const size_t smem = any ? ds->stack_bytes : ds->inorder_stack_bytes;
+            const int blocks = out_mode == OUT_TAIL ? ds->inorder_tail_blocks : ds->inorder_blocks;
+            const size_t smem = ds->inorder_stack_bytes;
             const dim3 g(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(blocks), want)));
-#define RTP_LAUNCH_PERSISTENT(C, O, L, A) trace_persistent_kernel<C, O, L, A><<<g, block, smem, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta, no_index)
+#define RTP_LAUNCH_PERSISTENT(C, O, L) trace_persistent_kernel<C, O, L><<<g, block, smem, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, n_dev, ta, no_index)
 #define RTP_LAUNCH_PERSISTENT_O(O)                                                                   \
     do {                                                                                             \
-        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true, 0); else RTP_LAUNCH_PERSISTENT(false, O, true, 0); }     \
-        else if (any == 2) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 2); else RTP_LAUNCH_PERSISTENT(false, O, false, 2); } \
-        else if (any == 1) { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 1); else RTP_LAUNCH_PERSISTENT(false, O, false, 1); } \
-        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false, 0); else RTP_LAUNCH_PERSISTENT(false, O, false, 0); }        \
+        if (list) { if (count) RTP_LAUNCH_PERSISTENT(true, O, true); else RTP_LAUNCH_PERSISTENT(false, O, true); }     \
+        else { if (count) RTP_LAUNCH_PERSISTENT(true, O, false); else RTP_LAUNCH_PERSISTENT(false, O, false); }        \
     } while (0)
             if (out_mode == OUT_FULL) RTP_LAUNCH_PERSISTENT_O(OUT_FULL);
             else if (out_mode == OUT_WAVE) RTP_LAUNCH_PERSISTENT_O(OUT_WAVE);
@@ -2612,7 +2400,7 @@ static int render_enqueue(DeviceScene* ds, const rtp_camera* camera, const rtp_r
             RTP_CUDA(cudaMemsetAsync(ds->wave.count, 0, 130 * sizeof(unsigned long long), st));
             // segment 0 without a generate kernel: the pure any-order kernel makes its primary rays itself (GenArgs) and the shade
             // kernel regenerates them; other scenes (List roots, in-order walk) and tail-mode launches read them from queue 0
-            const bool fused_gen = ds->view.root_kind == RTP_ROOT_BVH && ds->any_order && !ds->use_combined && !ds->no_fused_gen &&
+            const bool fused_gen = ds->view.root_kind == RTP_ROOT_BVH && ds->any_order && !ds->no_fused_gen &&
                                    !(ds->tail_threshold && total <= ds->tail_threshold);
             const GenArgs ga{cam, rp};
             if (!fused_gen) {

@@ -859,15 +859,13 @@ def test_any_order_walk_renders_match_oracle(gpu, monkeypatch, name, w, h, spp):
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("variant", ["1", "2"])
-def test_any_order_stack_overflow_hands_the_ray_to_the_in_order_walk(gpu, monkeypatch, variant):
-    """the any-order stack is capped per lane; a lane that cannot postpone three more children gives its ray to the in-order
-    walk. With the cap forced down to the tree depth most incoherent rays overflow: same bits, many re-walks. Both builds
-    of the kernel (5 and 4 resident blocks per SM)."""
+def test_any_order_stack_overflow_hands_the_ray_to_the_in_order_walk(gpu, monkeypatch):
+    """the any-order stack is capped per lane; a lane that cannot postpone three more children defers its ray to the in-order
+    kernel (second launch over the defer list; inside the integrator: the shading thread's exact walk). With the cap forced down
+    to four entries most incoherent rays overflow: same bits, many deferred rays."""
     import torch
 
     monkeypatch.setenv("RTP_TRAVERSAL", "any")
-    monkeypatch.setenv("RTP_ANY_VARIANT", variant)
     sc = scenes.bunny_lambert()
     rays = _mixed_rays(sc)
     o = oracle.Scene(sc)
