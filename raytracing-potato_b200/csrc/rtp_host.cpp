@@ -884,6 +884,7 @@ struct ObjCornerHash {
 struct Cursor {
     const char* p;
     const char* end;
+    bool zero_index = false;  // a face corner named index 0: OBJ indices are 1-based, the reference's `- 1` (mesh.rs:64-69) underflows and panics
     bool blank() const { return p < end && (*p == ' ' || *p == '\t'); }
     // nom `space1`
     bool space1() {
@@ -926,6 +927,8 @@ struct Cursor {
             break;
         }
         if (!have[0]) return false;
+        for (int k = 0; k < 3; ++k)
+            if (have[k] && val[k] == 0) zero_index = true;
         out->p = val[0] - 1;
         out->t = have[1] ? val[1] - 1 : RTP_MISS;
         out->n = have[2] ? val[2] - 1 : RTP_MISS;
@@ -972,6 +975,7 @@ static int obj_load(const char* path, rtp_mesh* out) {
                     ++count;
                     if (!c.space1()) break;
                 }
+                if (c.zero_index) return set_error(RTP_ERR_FORMAT, "OBJ face with index 0: indices are 1-based (mesh.rs:64-69 would underflow)");
                 if (count) faces.emplace_back(first, count);
             }
         }

@@ -1054,3 +1054,41 @@ def test_c5_full_field_sampled_rays_equal_oracle(gpu):
     sl = (slice(tile[1], tile[1] + tile[3]), slice(tile[0], tile[0] + tile[2]))
     assert np.sqrt(((ig[sl] - io[sl]) ** 2).mean()) <= IMG_RMSE and (fg[sl] == fo[sl]).all()
     g.close(); o.close()
+
+
+def test_many_concurrent_launches_on_many_streams(gpu):
+    """rtp_trace_closest_device from more streams than the library has launch slots (8): every launch owns a work queue and a defer
+    list for its lifetime (a slot's next user waits on the event of its last launch), so launches in flight on different streams never
+    share them. 24 streams x 4 rounds of different batches — primary, incoherent, and one with axis-parallel rays that are deferred
+    to the in-order kernel — must each return the bits of the same batch traced alone."""
+    import torch
+
+    sc = scenes.bunny_lambert()
+    cam = api.Camera(16 / 9, sc.camera.fov, sc.camera.focal_dist, 0.0, sc.camera.transformation)
+    primary = api.camera_rays(cam, 320, 180)
+    axis = primary[:20000].copy()
+    axis["direction"][::3] = [0.0, -1.0, 0.0]  # not eligible for the f32 walk: deferred
+    batches = [primary, scenes.incoherent_rays(70000), axis, scenes.incoherent_rays(30000, first=10 ** 6)]
+    with api.Scene(sc) as g:
+        d_rays = [torch.from_numpy(b.view(np.float64).reshape(-1, 8)).cuda() for b in batches]
+        want = []
+        for r in d_rays:
+            h = torch.empty((r.shape[0], 2), dtype=torch.float64, device="cuda")
+            g.hit_device(r.data_ptr(), r.shape[0], h.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            want.append(h.clone())
+        streams = [torch.cuda.Stream() for _ in range(24)]
+        outs = [[torch.empty_like(want[k % len(batches)]) for k in range(4)] for _ in streams]
+        torch.cuda.synchronize()
+        for rnd in range(4):
+            for s_i, st in enumerate(streams):
+                k = (s_i + rnd) % len(batches)
+                out = outs[s_i][rnd]
+                if out.shape != want[k].shape:
+                    outs[s_i][rnd] = out = torch.empty_like(want[k])
+                g.hit_device(d_rays[k].data_ptr(), d_rays[k].shape[0], out.data_ptr(), st.cuda_stream)
+        torch.cuda.synchronize()
+        for rnd in range(4):
+            for s_i in range(len(streams)):
+                k = (s_i + rnd) % len(batches)
+                assert bool((outs[s_i][rnd].view(torch.int64) == want[k].view(torch.int64)).all()), (s_i, rnd, k)

@@ -117,6 +117,13 @@ def test_obj_parser_subset(tmp_path):
     with pytest.raises(api.RtpError) as e3:
         api.obj.load(str(tmp_path / "missing.obj"))
     assert e3.value.code == A.ERR_IO
+    # OBJ indices are 1-based: the reference's `index - 1` (mesh.rs:64-69) underflows on a 0 and panics; the loader must not
+    # quietly read it as "no normal / no uv"
+    for face in ("f 1/0/0 2 3", "f 0 1 2", "f 1//0 2//1 3//1"):
+        p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nvt 0 0\n" + face + "\n")
+        with pytest.raises(api.RtpError) as e4:
+            api.obj.load(str(p))
+        assert e4.value.code == A.ERR_FORMAT, face
 
 
 def test_bunny_obj_roundtrip_through_text(tmp_path):
