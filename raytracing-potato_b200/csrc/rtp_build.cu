@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(128) collapse_write_kernel(const DNode* __rest
 
 void device_free_arrays(DevArrays* a) {
     if (!a || !a->valid) return;
+    if (a->adopted) { *a = DevArrays{}; return; }  // a DeviceScene owns them
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(a->device);

@@ -1374,23 +1374,30 @@ __device__ __forceinline__ double2 ldg_stream2(const double* p) {
 
 constexpr uint32_t kAnyStride = 128u * 8u;  // bytes between two levels of a thread's stack column ([entry][thread] of uint2)
 
-// per-ray slack coefficients from scalars; false: not eligible
+// per-ray eligibility and slack coefficients from scalars; false: the ray goes to the in-order kernel.
+// Everything is evaluated in f32 with every operation rounded up (all quantities are non-negative), so the slack is an upper bound of
+// the real-number expression in DESIGN.md 4b; the magnitudes are converted first and maximised in f32 (RU is monotone, so that
+// equals converting the f64 maximum), which also serves the range checks of the f32 walk: finite origin with |o| <= 1e15 and
+// 1e-15 <= |1/d| <= 1e15 on every axis (the float thresholds sit just inside the f64 ones, and a NaN fails every comparison).
 __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D3 inv, double tmin, float& s0f, float& s1f) {
-    const float u = 0x1.0p-53f, K = 8.9e-9f;
-    const float Po = __double2float_ru(fmax(fmax(fabs(o.x), fabs(o.y)), fabs(o.z)));
+    const float u = 0x1.0p-53f, K = 8.9e-9f;  // K >= 8 u 1e7: |det| >= 1e-7 (hittable.rs:80), 8u: rounding of a 6-term sum of products
+    const float Po = fmaxf(fmaxf(__double2float_ru(fabs(o.x)), __double2float_ru(fabs(o.y))), __double2float_ru(fabs(o.z)));
+    const float D = fmaxf(fmaxf(__double2float_ru(fabs(d.x)), __double2float_ru(fabs(d.y))), __double2float_ru(fabs(d.z)));
+    const float I = fmaxf(fmaxf(__double2float_ru(fabs(inv.x)), __double2float_ru(fabs(inv.y))), __double2float_ru(fabs(inv.z)));
+    const float Imin = fminf(fminf(__double2float_rd(fabs(inv.x)), __double2float_rd(fabs(inv.y))), __double2float_rd(fabs(inv.z)));
+    const bool in_range = (Po <= 1e15f) & (I <= 1e15f) & (Imin >= 1.0000001e-15f);
     const float P = __fadd_ru(Po, sc.any_Af);
-    const float D = __double2float_ru(fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z)));
-    const float I = __double2float_ru(fmax(fmax(fabs(inv.x), fabs(inv.y)), fabs(inv.z)));
     const float E = sc.any_Ef;
     const float E2 = __fmul_ru(E, E), DE2 = __fmul_ru(D, E2), PE = __fmul_ru(P, E);
     const float kappa = __fmul_ru(__fmul_ru(K, 6.0f), DE2);
     const float e_uv = __fadd_ru(__fmul_ru(K, __fadd_ru(__fmul_ru(6.0f, __fmul_ru(PE, D)), __fmul_ru(6.06f, DE2))), 3.0f * u);
     const float eta = __fmul_ru(__fadd_ru(__fmul_ru(4.0f, e_uv), 5.0f * u), E);
+    // 1 / (1 - kappa) <= 4/3 for kappa <= 1/4: no divide on the per-ray path; the factor 4 in front absorbs the second-order terms
     const float a0 = __fmul_ru(__fmul_ru(__fadd_ru(eta, __fmul_ru(u, P)), I), 1.0000002f);
     const float a1 = __fmul_ru(__fmul_ru(__fmul_ru(K, 6.0f), __fmul_ru(PE, E)), 1.3333334f);
     const float a2 = __fmul_ru(3.0f * u, __double2float_ru(fabs(tmin)));
     float a3 = 0.f;
-    if (sc.any_Rf >= 0.f) {  // scene-uniform branch
+    if (sc.any_Rf >= 0.f) {  // scene-uniform branch: spheres that are not big (DESIGN.md 4b "Spheres")
         const float oc = __fadd_ru(Po, sc.any_Cf);
         const float S = __fadd_ru(__fmul_ru(3.0f, __fmul_ru(oc, oc)), __fmul_ru(sc.any_Rf, sc.any_Rf));
         const float g = __fsqrt_ru(__fmul_ru(40.0f * u, S));
@@ -1398,7 +1405,7 @@ __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D
     }
     s0f = __fmul_ru(4.0f, __fadd_ru(__fadd_ru(__fadd_ru(a0, a1), a2), a3));
     s1f = __fmul_ru(4.0f, __fadd_ru(__fmul_ru(__fadd_ru(__fmul_ru(__fmul_ru(K, 6.0f), DE2), 5.0f * u), 1.3333334f), 8.0f * u));
-    return (kappa <= 0.25f) & (e_uv <= 0.01f) & (s0f <= 3.0e38f) & (s1f <= 3.0e38f);
+    return in_range & (kappa <= 0.25f) & (e_uv <= 0.01f) & (s0f <= 3.0e38f) & (s1f <= 3.0e38f);
 }
 
 #ifndef RTP_ANY_BLOCKS
@@ -1409,6 +1416,9 @@ __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D
 #endif
 #ifndef RTP_ANY_POPLOOP
 #define RTP_ANY_POPLOOP 1 // 1: a step pops until it has a node to visit (0: one stack entry per step)
+#endif
+#ifndef RTP_ANY_BRANCHY_PUSH
+#define RTP_ANY_BRANCHY_PUSH 0  // 1: round 2's first version, nested branches around the three pushes
 #endif
 #ifndef RTP_ANY_PICK
 #define RTP_ANY_PICK 1    // 1: a round tests leaves first when more lanes wait for a leaf test than can walk
@@ -1543,11 +1553,9 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                         tmin = r3.x; tmax = r3.y;
                     }
                     inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
-                    // eligibility (walker_start + any_begin): finite origin, 1e-15 <= |1/d| <= 1e15 on every axis, |o| <= 1e15,
-                    // 0 <= t_min <= t_max, self-consistent slack
-                    bool ok = in_f32_range(inv.x) & in_f32_range(inv.y) & in_f32_range(inv.z) & (fabs(o.x) <= 1e15) & (fabs(o.y) <= 1e15) &
-                              (fabs(o.z) <= 1e15) & (tmax >= tmin) & (tmin >= 0.0);
-                    ok = ok & any_slack_of(sc, o, d, inv, tmin, s0f, s1f);
+                    // eligibility: finite origin, 1e-15 <= |1/d| <= 1e15 on every axis, |o| <= 1e15 and a self-consistent slack
+                    // (any_slack_of), 0 <= t_min <= t_max
+                    const bool ok = any_slack_of(sc, o, d, inv, tmin, s0f, s1f) & (tmax >= tmin) & (tmin >= 0.0);
                     if (ok || OUT == OUT_WAVE) lc.rays++;  // a ray deferred to the in-order kernel is counted there
                     if (!ok) {
                         if (OUT == OUT_WAVE) {
@@ -1653,6 +1661,7 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                     const uint32_t s1 = min(m0, m1), s2 = max(m0, m1);
 #define RTP_SEL(k) (((k) & 2u) ? (((k) & 1u) ? ch.w : ch.z) : (((k) & 1u) ? ch.y : ch.x))
                     node = kNone;
+#if RTP_ANY_BRANCHY_PUSH
                     if (s1 != 0xFFFFFFFFu) {  // the keys are sorted: without a second child there is no third or fourth
                         if (sp > slimit) {
                             // no room to postpone three children: give the ray to the in-order kernel
@@ -1665,6 +1674,24 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                             sts_v2(sp, RTP_SEL(s1), s1 & ~3u); sp += kAnyStride;
                         }
                     }
+#else
+                    {
+                        // the three farther children, farthest first, without branches: every lane writes its three candidate entries
+                        // at consecutive positions and advances the stack top only past the ones that exist (the keys are sorted:
+                        // an absent child is never followed by a present one). Incoherent rays ran the nested pushes at 2-7 lanes.
+                        const bool p1 = s1 != 0xFFFFFFFFu, p2 = s2 != 0xFFFFFFFFu, p3 = s3 != 0xFFFFFFFFu;
+                        if (p1 & (sp > slimit)) {
+                            // no room to postpone three children: give the ray to the in-order kernel
+                            A_min = -CUDART_INF_F; sp = sbase; leaf0 = 0u; leaf1 = 0u; s0 = 0xFFFFFFFFu;
+                        } else {
+                            const uint32_t a3 = sp, a2 = a3 + (p3 ? kAnyStride : 0u), a1 = a2 + (p2 ? kAnyStride : 0u);
+                            if (p3) sts_v2(a3, RTP_SEL(s3), s3 & ~3u);
+                            if (p2) sts_v2(a2, RTP_SEL(s2), s2 & ~3u);
+                            if (p1) sts_v2(a1, RTP_SEL(s1), s1 & ~3u);
+                            sp = a1 + (p1 ? kAnyStride : 0u);
+                        }
+                    }
+#endif
                     if (s0 != 0xFFFFFFFFu) {
                         const uint32_t c = RTP_SEL(s0);
                         if (c & kWideLeaf) {
@@ -1944,14 +1971,21 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
     ds->device = device;
     auto bail = [&](int code) { device_scene_free(ds); return code; };
     // arrays built on a device (rtp_build.cu) are adopted there and copied peer to peer elsewhere; host-built ones are uploaded
+    const bool adopt = flat.dev.valid && flat.dev.device == device && !flat.dev.adopted;  // the replica on the building device takes the arrays over
     auto take = [&](auto** dst, auto* src, size_t count) -> int {
         using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dst)>>;
         const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-        RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
-        if (count) RTP_CUDA(cudaMemcpyPeer(*dst, device, src, flat.dev.device, count * sizeof(T)));
+        if (!adopt) {
+            RTP_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), bytes));
+            if (count) RTP_CUDA(cudaMemcpyPeer(*dst, device, src, flat.dev.device, count * sizeof(T)));
+        }
         ds->bytes += bytes;
         return RTP_OK;
     };
+    if (adopt) {  // all five at once, so that a failure further down frees each array exactly once (with this DeviceScene)
+        ds->nodes = flat.dev.nodes; ds->wide = flat.dev.wide; ds->wide_boxes = flat.dev.wide_boxes; ds->prims = flat.dev.prims; ds->attrs = flat.dev.attrs;
+        flat.dev.adopted = true;
+    }
     if (flat.dev.valid) {
         if ((rc = take(&ds->nodes, flat.dev.nodes, flat.dev.n_nodes)) != RTP_OK) return bail(rc);
         if ((rc = take(&ds->wide, flat.dev.wide, flat.dev.n_wide)) != RTP_OK) return bail(rc);

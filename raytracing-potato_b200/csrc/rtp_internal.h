@@ -132,6 +132,7 @@ constexpr uint32_t kMaxBig = 8;
 // adopts them on that device and copies them peer to peer to the other devices of a multi-device scene.
 struct DevArrays {
     bool valid = false;
+    mutable bool adopted = false;  // the replica on `device` owns the arrays now (device_scene_upload); the others copied from them
     int device = -1;
     DNode* nodes = nullptr; size_t n_nodes = 0;
     DWide* wide = nullptr; double* wide_boxes = nullptr; size_t n_wide = 0;
