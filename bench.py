@@ -696,6 +696,31 @@ def multi_device_leg(ctx, sc, rw, rh, spp):
                    "collective": "none: rows round-robin over devices, each device copies its rows to the host frame"}
             rgb.free()
             multi.close()
+            # the C2 batch through ONE rtp_trace_closest call: its 256 Ki-ray chunks are dealt out over the devices, so every
+            # device's host link carries a share of the 80 B/ray stream
+            from rtp_b200 import _abi as A2
+
+            scb = ctx.scenes.bunny_lambert()
+            camb = api.Camera(W / H, scb.camera.fov, scb.camera.focal_dist, 0.0, scb.camera.transformation)
+            h_rays = api.PinnedBuffer((N_RAYS,), A2.RAY_DTYPE)
+            h_hits = api.PinnedBuffer((N_RAYS,), A2.HIT_DTYPE)
+            h_rays.array[:] = api.camera_rays(camb, W, H)
+            rates = {}
+            for mask_n in (1, world):
+                with api.Scene(scb, device_mask=(1 << mask_n) - 1) as sb:
+                    sb.hit(h_rays.array, out=h_hits.array)
+                    t0 = time.perf_counter()
+                    reps = 10
+                    for _ in range(reps):
+                        sb.hit(h_rays.array, out=h_hits.array)
+                    rates[mask_n] = reps * N_RAYS / (time.perf_counter() - t0) / 1e6
+                    if mask_n == 1:
+                        ref_hits = h_hits.array.copy()
+            res["trace_closest_host_buffers"] = {"mrays_per_s_1_device": rates[1], f"mrays_per_s_{world}_devices": rates[world], "speedup": rates[world] / rates[1],
+                                                 "bit_identical_to_1_device": bool(ref_hits.tobytes() == h_hits.array.tobytes()),
+                                                 "api": "rtp_trace_closest on a multi-device scene (pinned host buffers)"}
+            h_rays.free()
+            h_hits.free()
         except Exception as e:  # noqa: BLE001 - the leg is reported as failed, the headline stands
             res = {"error": f"{type(e).__name__}: {e}"}
     ctx.dist.barrier(group=ctx.cpu_group)  # the waiting ranks sit in a gloo (host) barrier: their GPUs stay idle for rank 0
