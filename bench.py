@@ -486,6 +486,16 @@ def main():
     d_rays[1].copy_(d_rays[0])
     d_hits = torch.empty((N_RAYS, 2), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    # the numpy camera that makes the shifted N > 1 batches is the device camera kernel bit for bit (checked at the unshifted centre)
+    inputs_ok = None
+    if rank == 0:
+        i = np.tile(np.arange(W, dtype=np.float64), H)
+        j = np.repeat(np.arange(H, dtype=np.float64), W)
+        centre = torch.empty((N_RAYS, 8), dtype=torch.float64, device=dev)
+        api.camera_rays_device(cam, W, H, centre.data_ptr(), stream)
+        torch.cuda.synchronize()
+        inputs_ok = bool(centre.cpu().numpy().tobytes() == _camera_rays_numpy(cam, (i + 0.5) / W, (j + 0.5) / H).tobytes())
+        del centre
 
     # --- value: device-resident batch, CUDA events on the launching stream ------------------------------------------------
     k_ = [0]
@@ -626,6 +636,7 @@ def main():
             "rays_per_step_per_gpu": N_RAYS, "sharding": "rank r traces sub-sample r of a world-times supersampled primary batch; no data-path collective",
             "l2": "inputs larger than L2: two 132.7 MB ray buffers are rotated between steps (265 MB > 126 MB L2); no flush needed",
             "host_cores_bound_per_rank": affinity, "host_cores_bound_how": affinity_how,
+            "inputs": "rays made by camera_rays_kernel (N = 1) / by its numpy restatement at shifted pixel centres (N > 1)", "numpy_camera_equals_device_kernel_bits": inputs_ok,
         },
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": N_RAYS * RAY_BYTES, "d2h_bytes_per_step": N_RAYS * HIT_BYTES,
                 "steps": e2e_steps, "api": "rtp_trace_closest (pinned host buffers, 256Ki-ray chunks on 3 streams)", "gpu_launches_per_step": e2e_launches,
