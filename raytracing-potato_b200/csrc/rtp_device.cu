@@ -1414,8 +1414,11 @@ __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D
 #ifndef RTP_ANY_STEPS
 #define RTP_ANY_STEPS 2   // walk steps per round of votes
 #endif
+#ifndef RTP_ANY_PREFETCH
+#define RTP_ANY_PREFETCH 2 // L2 prefetch distance of the ray stream, in quarters of (warps of the grid) x (rays per reservation); 0: off
+#endif
 #ifndef RTP_ANY_POPLOOP
-#define RTP_ANY_POPLOOP 1 // 1: a step pops until it has a node to visit (0: one stack entry per step)
+#define RTP_ANY_POPLOOP 2 // stack entries a step may take before it visits a node (1: one per step, as in the first version)
 #endif
 #ifndef RTP_ANY_BRANCHY_PUSH
 #define RTP_ANY_BRANCHY_PUSH 0  // 1: round 2's first version, nested branches around the three pushes
@@ -1536,8 +1539,17 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (base + static_cast<unsigned long long>(cnt) >= n) more = false;
                 const int rank = __popc(free_mask & lt_mask);
-                const size_t i = static_cast<size_t>(base) + rank;
-                if (!busy && rank < cnt && i < n) {
+#if RTP_ANY_PREFETCH
+                if (!GEN) {
+                    // the ray stream comes from HBM and the first thing a refill does with a ray is divide by its direction: pull the
+                    // rays some warp will take about one refill from now into L2 (a quarter of the grid's warps x 32 rays up the queue
+                    // per unit of RTP_ANY_PREFETCH). Stateless: the queue is handed out in order, whoever takes them finds them there.
+                    const unsigned long long pf = base + static_cast<unsigned long long>(RTP_ANY_PREFETCH) * (n_warps / 4) * 32ull + static_cast<unsigned>(rank);
+                    if (!busy && rank < cnt && pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(rays + pf));
+                }
+#endif
+                const uint32_t i = (!busy && rank < cnt && base + static_cast<unsigned>(rank) < n) ? static_cast<uint32_t>(base) + static_cast<uint32_t>(rank) : 0xFFFFFFFFu;
+                if (i != 0xFFFFFFFFu) {
                     double tmax;
                     if (GEN) {
                         uint32_t gi, gj, gs;
@@ -1562,10 +1574,10 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                             reinterpret_cast<double2*>(static_cast<WaveHit*>(out) + i)[1] = make_double2(0.0, __hiloint2double(0, static_cast<int>(kDeferredHit)));
                         } else {
                             const unsigned long long slot = atomicAdd(defer.count, 1ull);
-                            defer.idx[slot] = static_cast<uint32_t>(i);
+                            defer.idx[slot] = i;
                         }
                     } else {
-                        idx = static_cast<uint32_t>(i);
+                        idx = i;
                         sx = inv.x < 0.0; sy = inv.y < 0.0; sz = inv.z < 0.0;
                         const double px = o.x * inv.x, py = o.y * inv.y, pz = o.z * inv.z;
                         const double kx = fabs(px) * 0x1.0p-21 + 1e-37, ky = fabs(py) * 0x1.0p-21 + 1e-37, kz = fabs(pz) * 0x1.0p-21 + 1e-37;
@@ -1614,20 +1626,18 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
         for (int rep = 0; rep < RTP_ANY_STEPS; ++rep) {
             if ((leaf1 == 0u) & ((node != kNone) | (sp != sbase))) {
                 // take postponed entries until one gives a node to visit: leaves go to the pending pair, entries beyond the window are
-                // dropped. (One entry per step left half of the step slots of incoherent rays without a node: RTP_LANE_STATS.)
-                while ((node == kNone) & (sp != sbase) & (leaf1 == 0u)) {
+                // dropped. (One entry per step left half of the step slots of incoherent rays without a node: RTP_LANE_STATS; an
+                // unbounded loop runs its late iterations for three or four lanes: RTP_ANY_POPLOOP bounds the pops per step.)
+#pragma unroll 1
+                for (int pops = 0; pops < RTP_ANY_POPLOOP && ((node == kNone) & (sp != sbase) & (leaf1 == 0u)); ++pops) {
                     sp -= kAnyStride;
                     const uint2 e = lds_v2(sp);
-                    if (__uint_as_float(e.y) <= T_up) {  // else: the window shrank since this entry was postponed
-                        if (e.x & kWideLeaf) {
-                            if (leaf0 == 0u) leaf0 = e.x; else leaf1 = e.x;
-                        } else {
-                            node = e.x;
-                        }
-                    }
-#if !RTP_ANY_POPLOOP
-                    break;
-#endif
+                    const bool inside = __uint_as_float(e.y) <= T_up;  // else: the window shrank since this entry was postponed
+                    const bool is_leaf = (e.x & kWideLeaf) != 0u;
+                    const bool first = leaf0 == 0u;
+                    node = (inside & !is_leaf) ? e.x : kNone;
+                    leaf1 = (inside & is_leaf & !first) ? e.x : leaf1;
+                    leaf0 = (inside & is_leaf & first) ? e.x : leaf0;
                 }
                 if (node != kNone) {
                     const uint32_t nb = node * 8u;
@@ -1692,13 +1702,12 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                         }
                     }
 #endif
-                    if (s0 != 0xFFFFFFFFu) {
+                    {   // the nearest child: a node is visited next, a leaf joins the pending pair; selects only
                         const uint32_t c = RTP_SEL(s0);
-                        if (c & kWideLeaf) {
-                            if (leaf0 == 0u) leaf0 = c; else leaf1 = c;
-                        } else {
-                            node = c;
-                        }
+                        const bool valid = s0 != 0xFFFFFFFFu, is_leaf = (c & kWideLeaf) != 0u, first = leaf0 == 0u;
+                        node = (valid & !is_leaf) ? c : kNone;
+                        leaf1 = (valid & is_leaf & !first) ? c : leaf1;
+                        leaf0 = (valid & is_leaf & first) ? c : leaf0;
                     }
 #undef RTP_SEL
                 }
