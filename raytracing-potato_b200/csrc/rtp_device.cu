@@ -1366,6 +1366,23 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t a) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory"); }
+__device__ __forceinline__ uint32_t dlo(double x) { return static_cast<uint32_t>(__double2loint(x)); }
+__device__ __forceinline__ uint32_t dhi(double x) { return static_cast<uint32_t>(__double2hiint(x)); }
+__device__ __forceinline__ double mkd(uint32_t lo, uint32_t hi) { return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo)); }
 __device__ __forceinline__ double2 ldg_stream2(const double* p) {
     double2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -1373,6 +1390,12 @@ __device__ __forceinline__ double2 ldg_stream2(const double* p) {
 }
 
 constexpr uint32_t kAnyStride = 128u * 8u;  // bytes between two levels of a thread's stack column ([entry][thread] of uint2)
+// The part of a lane's state that only a hit, the set-up and the retirement touch lives in shared memory behind the stacks, as four
+// [chunk][thread] words of 16 bytes (conflict-free ld/st.shared.v4): 14 registers less in the walk, which is what lets six blocks
+// share an SM without spills.  0: 1/d.x, 1/d.y   1: 1/d.z, slack s0, slack s1 (floats)   2: best u, best v
+// 3: smallest abnormal t (float bits), ray index (0xFFFFFFFF: the lane holds no ray), -, -
+constexpr uint32_t kColdStride = 128u * 16u;
+constexpr size_t kAnyColdBytes = static_cast<size_t>(kColdStride) * 4u;
 
 // per-ray eligibility and slack coefficients from scalars; false: the ray goes to the in-order kernel.
 // Everything is evaluated in f32 with every operation rounded up (all quantities are non-negative), so the slack is an upper bound of
@@ -1409,7 +1432,7 @@ __device__ __forceinline__ bool any_slack_of(const DSceneView& sc, D3 o, D3 d, D
 }
 
 #ifndef RTP_ANY_BLOCKS
-#define RTP_ANY_BLOCKS 5  // resident blocks per SM the kernel is built for (register budget 65536 / (128 x blocks))
+#define RTP_ANY_BLOCKS 6  // resident blocks per SM the kernel is built for (register budget 65536 / (128 x blocks))
 #endif
 #ifndef RTP_ANY_STEPS
 #define RTP_ANY_STEPS 2   // walk steps per round of votes
@@ -1443,23 +1466,22 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t sbase = smem_u32(any_stack) + threadIdx.x * 8u;      // bottom of this thread's stack column
     const uint32_t slimit = sbase + (sc.any_cap - 3u) * kAnyStride;     // pushing three more entries above this would overflow
+    const uint32_t cold = smem_u32(any_stack) + sc.any_cap * kAnyStride + threadIdx.x * 16u;  // chunk 0 of this thread's cold state
     LocalCounters lc = {0, 0, 0, 0, 0, 0, 0};
+    sts_v4(cold + 3u * kColdStride, __float_as_uint(CUDART_INF_F), 0xFFFFFFFFu, 0u, 0u);
 
-    // ---- lane state -----------------------------------------------------------------------------------------------------------
-    D3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
+    // ---- lane state in registers (1/d, the slack coefficients, best u and v, the abnormal mark and the ray index are cold) ---------
+    D3 o = mk(0, 0, 0), d = mk(0, 0, 0);
     double tmin = 0.0;
-    double best_t = 0.0, best_u = 0.0, best_v = 0.0;  // closest normal hit so far (valid when best != kNoPrim)
+    double best_t = 0.0;                              // t of the closest normal hit so far (valid when best != kNoPrim)
     uint32_t best = kNoPrim;                          // slot | kind << 31
     double T_win = 0.0;                               // window top: min(ray.t_max, best_t + 2 slack(best_t))
-    float A_min = CUDART_INF_F;                       // smallest t of an abnormal leaf seen (rounded DOWN to f32: conservative)
-    float s0f = 0.f, s1f = 0.f;
     float ix = 0.f, iy = 0.f, iz = 0.f, clx = 0.f, cly = 0.f, clz = 0.f, chx = 0.f, chy = 0.f, chz = 0.f, tmin_dn = 0.f, T_up = 0.f;
-    uint32_t onx = 0, ony = 2, onz = 4, ofx = 1, ofy = 3, ofz = 5;  // float4 index of the near / far plane of each axis inside a node (DWide::plane)
+    uint32_t onx = 0, ony = 2, onz = 4;  // float4 index of the near plane of each axis inside a node (DWide::plane); the far plane is that index ^ 1
     bool sx = false, sy = false, sz = false;
     uint32_t node = kNone;        // node to visit next, or kNone: take the next stack entry
     uint32_t sp = sbase;          // shared-memory address of the first free entry of this thread's column
     uint32_t leaf0 = 0u, leaf1 = 0u;  // pending leaves (raw child words, oldest first); 0 = none (child word 0 is the root, never a leaf)
-    uint32_t idx = 0xFFFFFFFFu;   // ray held by this lane (index into rays / out), 0xFFFFFFFF = none
     bool more = true;             // warp-uniform: the queue may still hold rays
     const size_t n_warps = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
     const int lane_cap = static_cast<int>(min(static_cast<size_t>(32), max(static_cast<size_t>(tune.min_lanes), (n + n_warps - 1) / n_warps)));
@@ -1481,8 +1503,10 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
         }
         if (hit) {
             if (!(t == t)) {
-                A_min = -CUDART_INF_F;  // NaN t (overflowing geometry): let the in-order walk decide
+                sts_u32(cold + 3u * kColdStride, __float_as_uint(-CUDART_INF_F));  // NaN t (overflowing geometry): let the in-order walk decide
             } else {
+                const uint4 c0 = lds_v4(cold), c1 = lds_v4(cold + kColdStride);
+                const D3 inv = mk(mkd(c0.x, c0.y), mkd(c0.z, c0.w), mkd(c1.x, c1.y));
                 const double* pb = p->bmin;
                 const double2 b0 = ldg2(pb), b1 = ldg2(pb + 2), b2 = ldg2(pb + 4);
                 if (COUNT) lc.leaf_gates++;
@@ -1490,13 +1514,16 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                     // normal leaf: min t, ties to the larger DFS rank (= slot)
                     const uint32_t bslot = best & 0x7FFFFFFFu;
                     if (best == kNoPrim || t < best_t || (t == best_t && slot > bslot)) {
-                        best_t = t; best_u = u; best_v = v; best = slot | (kind << 31);
-                        const double win = t + 2.0 * (static_cast<double>(s0f) + static_cast<double>(s1f) * fabs(t));
+                        best_t = t; best = slot | (kind << 31);
+                        sts_v4(cold + 2u * kColdStride, dlo(u), dhi(u), dlo(v), dhi(v));
+                        const double win = t + 2.0 * (static_cast<double>(__uint_as_float(c1.z)) + static_cast<double>(__uint_as_float(c1.w)) * fabs(t));
                         T_win = fmin(T_win, win);
                         T_up = __double2float_ru(T_win);
                     }
                 } else if (collide_fast(b0, b1, b2, o, inv, sx, sy, sz, tmin, CUDART_INF)) {
-                    A_min = fminf(A_min, __double2float_rd(t));  // abnormal: its box is entered, but only after t
+                    // abnormal: its box is entered, but only after t (rounded DOWN to f32: conservative)
+                    const float a_min = __uint_as_float(lds_u32(cold + 3u * kColdStride));
+                    sts_u32(cold + 3u * kColdStride, __float_as_uint(fminf(a_min, __double2float_rd(t))));
                 }
             }
         }
@@ -1510,7 +1537,10 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
         const int n_busy = __popc(busy_mask);
         const int room = min(32 - n_busy, max(lane_cap - n_busy, 0));
         if (busy_mask == 0u || (more && room >= refill_thr)) {
+            const uint4 c3 = lds_v4(cold + 3u * kColdStride);
+            const uint32_t idx = c3.y;              // ray held by this lane (index into rays / out), 0xFFFFFFFF = none
             if (!busy && idx != 0xFFFFFFFFu) {
+                const float A_min = __uint_as_float(c3.x);
                 // the walk of this lane's ray is over. An abnormal leaf inside the final window: the answer may depend on the
                 // reference's visiting order, the in-order kernel decides (A_min was rounded down, T_win compared in f64: conservative)
                 if (A_min != CUDART_INF_F && static_cast<double>(A_min) <= T_win) {
@@ -1523,11 +1553,12 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                     }
                     if (COUNT) lc.rewalks++;
                 } else {
+                    const uint4 c2 = lds_v4(cold + 2u * kColdStride);
                     HitRec h;
-                    h.t = best_t; h.u = best_u; h.v = best_v; h.slot = best == kNoPrim ? kNoPrim : (best & 0x7FFFFFFFu); h.kind = best >> 31;
+                    h.t = best_t; h.u = mkd(c2.x, c2.y); h.v = mkd(c2.z, c2.w); h.slot = best == kNoPrim ? kNoPrim : (best & 0x7FFFFFFFu); h.kind = best >> 31;
                     write_hit<OUT>(sc, out, idx, o, d, h);
                 }
-                idx = 0xFFFFFFFFu;
+                sts_u32(cold + 3u * kColdStride + 4u, 0xFFFFFFFFu);
             }
             if (!more) {
                 if (busy_mask == 0u) break;
@@ -1564,7 +1595,8 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                         o = mk(r0.x, r0.y, r1.x); d = mk(r1.y, r2.x, r2.y);
                         tmin = r3.x; tmax = r3.y;
                     }
-                    inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
+                    const D3 inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);  // utility.rs:71-77 Ray::expand
+                    float s0f, s1f;
                     // eligibility: finite origin, 1e-15 <= |1/d| <= 1e15 on every axis, |o| <= 1e15 and a self-consistent slack
                     // (any_slack_of), 0 <= t_min <= t_max
                     const bool ok = any_slack_of(sc, o, d, inv, tmin, s0f, s1f) & (tmax >= tmin) & (tmin >= 0.0);
@@ -1577,7 +1609,10 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                             defer.idx[slot] = i;
                         }
                     } else {
-                        idx = i;
+                        sts_v4(cold, dlo(inv.x), dhi(inv.x), dlo(inv.y), dhi(inv.y));
+                        sts_v4(cold + kColdStride, dlo(inv.z), dhi(inv.z), __float_as_uint(s0f), __float_as_uint(s1f));
+                        sts_v4(cold + 2u * kColdStride, 0u, 0u, 0u, 0u);
+                        sts_v4(cold + 3u * kColdStride, __float_as_uint(CUDART_INF_F), i, 0u, 0u);
                         sx = inv.x < 0.0; sy = inv.y < 0.0; sz = inv.z < 0.0;
                         const double px = o.x * inv.x, py = o.y * inv.y, pz = o.z * inv.z;
                         const double kx = fabs(px) * 0x1.0p-21 + 1e-37, ky = fabs(py) * 0x1.0p-21 + 1e-37, kz = fabs(pz) * 0x1.0p-21 + 1e-37;
@@ -1586,10 +1621,8 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                         chx = __double2float_ru(-px + kx); chy = __double2float_ru(-py + ky); chz = __double2float_ru(-pz + kz);
                         tmin_dn = __double2float_rd(tmin);
                         onx = sx ? 1u : 0u; ony = sy ? 3u : 2u; onz = sz ? 5u : 4u;
-                        ofx = sx ? 0u : 1u; ofy = sy ? 2u : 3u; ofz = sz ? 4u : 5u;
-                        best = kNoPrim; best_t = tmax; best_u = 0.0; best_v = 0.0;
+                        best = kNoPrim; best_t = tmax;
                         T_win = tmax; T_up = __double2float_ru(tmax);
-                        A_min = CUDART_INF_F;
                         leaf0 = 0u; leaf1 = 0u; sp = sbase;
                         node = 0u;
                         // the big primitives first, all lanes of the refill together
@@ -1644,9 +1677,9 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                     const float4 nx4 = __ldg(tree + (nb + onx));
                     const float4 ny4 = __ldg(tree + (nb + ony));
                     const float4 nz4 = __ldg(tree + (nb + onz));
-                    const float4 fx4 = __ldg(tree + (nb + ofx));
-                    const float4 fy4 = __ldg(tree + (nb + ofy));
-                    const float4 fz4 = __ldg(tree + (nb + ofz));
+                    const float4 fx4 = __ldg(tree + ((nb + onx) ^ 1u));
+                    const float4 fy4 = __ldg(tree + ((nb + ony) ^ 1u));
+                    const float4 fz4 = __ldg(tree + ((nb + onz) ^ 1u));
                     const uint4 ch = __ldg(reinterpret_cast<const uint4*>(tree + (nb + 6u)));
                     // key = conservative entry distance (non-negative float: its bits order like the value) with the child index in the
                     // two low bits; a child that is missed, beyond the window or empty gets the largest key
@@ -1660,6 +1693,8 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                         lc.node_visits++;
                         const double* b64 = sc.any_boxes + static_cast<size_t>(node) * 24;
                         const uint32_t keys[4] = {kx, ky, kz, kw};
+                        const uint4 c0 = lds_v4(cold), c1 = lds_v4(cold + kColdStride);
+                        const D3 inv = mk(mkd(c0.x, c0.y), mkd(c0.z, c0.w), mkd(c1.x, c1.y));
                         for (uint32_t k = 0; k < 4; ++k)  // a rejected child must fail the exact test with the window top as t_max
                             if (keys[k] == 0xFFFFFFFFu && (&ch.x)[k] != kWideEmpty &&
                                 collide_literal(ldg2(b64 + 6 * k), ldg2(b64 + 6 * k + 2), ldg2(b64 + 6 * k + 4), o, inv, tmin, T_win))
@@ -1675,7 +1710,7 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                     if (s1 != 0xFFFFFFFFu) {  // the keys are sorted: without a second child there is no third or fourth
                         if (sp > slimit) {
                             // no room to postpone three children: give the ray to the in-order kernel
-                            A_min = -CUDART_INF_F; sp = sbase; leaf0 = 0u; leaf1 = 0u; s0 = 0xFFFFFFFFu;
+                            sts_u32(cold + 3u * kColdStride, __float_as_uint(-CUDART_INF_F)); sp = sbase; leaf0 = 0u; leaf1 = 0u; s0 = 0xFFFFFFFFu;
                         } else {
                             if (s2 != 0xFFFFFFFFu) {
                                 if (s3 != 0xFFFFFFFFu) { sts_v2(sp, RTP_SEL(s3), s3 & ~3u); sp += kAnyStride; }
@@ -1692,7 +1727,7 @@ __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneVi
                         const bool p1 = s1 != 0xFFFFFFFFu, p2 = s2 != 0xFFFFFFFFu, p3 = s3 != 0xFFFFFFFFu;
                         if (p1 & (sp > slimit)) {
                             // no room to postpone three children: give the ray to the in-order kernel
-                            A_min = -CUDART_INF_F; sp = sbase; leaf0 = 0u; leaf1 = 0u; s0 = 0xFFFFFFFFu;
+                            sts_u32(cold + 3u * kColdStride, __float_as_uint(-CUDART_INF_F)); sp = sbase; leaf0 = 0u; leaf1 = 0u; s0 = 0xFFFFFFFFu;
                         } else {
                             const uint32_t a3 = sp, a2 = a3 + (p3 ? kAnyStride : 0u), a1 = a2 + (p2 ? kAnyStride : 0u);
                             if (p3) sts_v2(a3, RTP_SEL(s3), s3 & ~3u);
@@ -1876,7 +1911,7 @@ struct DeviceScene {
     int inorder_blocks = 0, inorder_tail_blocks = 0;  // grids of the in-order kernel (batch / tail mode)
     size_t inorder_stack_bytes = 0;
     int any_blocks = 0;                // grid of trace_any_kernel
-    size_t any_stack_bytes = 0;        // its dynamic shared memory: any_cap x 128 threads x 8 B
+    size_t any_stack_bytes = 0;        // its dynamic shared memory: any_cap x 128 threads x 8 B of stacks + 8 KiB of cold lane state
     int any_order = 0;                 // != 0: eligible rays take the any-order walk (RTP_TRAVERSAL); 2 marks a scene of >= 262,144 leaves
     uint32_t any_cap = 0;              // any-order stack entries per lane
     bool use_simple_kernel = false;    // RTP_TRACE_KERNEL=simple
@@ -2065,11 +2100,18 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         if (ds->any_order) {
             // any-order lanes postpone up to three siblings per level, each with its entry distance (8 B): a primary ray of the bunny
             // never holds more than 16 entries (gpurun_out/r2_sweep1.log: 0 overflows of 2 M rays at 16, 65 of 4 Mi incoherent ones),
-            // deep trees get up to 32; a lane that would need more defers its ray to the in-order kernel
+            // deep trees get up to 28 (a primary ray of the 2.5 M-leaf bunny field runs 4 % FASTER at 24 than at 32: occupancy, not
+            // overflows, is what the cap costs); a lane that would need more defers its ray to the in-order kernel
             const uint32_t any_depth = ds->free_wide ? flat.free_depth : flat.wide_depth;
-            ds->any_cap = std::max<uint32_t>(4u, std::min<uint32_t>(3u * any_depth + 1u, any_depth <= 12 ? 20u : 32u));
+            ds->any_cap = std::max<uint32_t>(4u, std::min<uint32_t>(3u * any_depth + 1u, any_depth <= 12 ? 20u : 28u));  // 28 x 1 KiB + 8 KiB of cold state: six blocks still fit one SM
             if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = static_cast<uint32_t>(std::max(4, std::min(48, std::atoi(v))));  // tests
-            ds->any_stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2);
+            ds->any_stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2) + kAnyColdBytes;  // the stacks, then the cold state
+            if (ds->any_stack_bytes > 48u * 1024u) {  // deep trees: above the default limit of dynamic shared memory, every instantiation that is launched
+#define RTP_ANY_SMEM(C, O, G) if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_any_kernel<C, O, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ds->any_stack_bytes))
+                RTP_ANY_SMEM(false, OUT_HIT, false); RTP_ANY_SMEM(true, OUT_HIT, false); RTP_ANY_SMEM(false, OUT_FULL, false); RTP_ANY_SMEM(true, OUT_FULL, false);
+                RTP_ANY_SMEM(false, OUT_WAVE, false); RTP_ANY_SMEM(true, OUT_WAVE, false); RTP_ANY_SMEM(false, OUT_WAVE, true); RTP_ANY_SMEM(true, OUT_WAVE, true);
+#undef RTP_ANY_SMEM
+            }
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&any_per_sm, trace_any_kernel<false, OUT_HIT, false>, 128, ds->any_stack_bytes);
             ds->any_blocks = prop.multiProcessorCount * std::max(any_per_sm, 1);
         }
