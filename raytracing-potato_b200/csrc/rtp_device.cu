@@ -2099,11 +2099,12 @@ int device_scene_upload(const FlatScene& flat, int device, DeviceScene** out) {
         ds->inorder_tail_blocks = prop.multiProcessorCount * std::max(tail_per_sm, 1);
         if (ds->any_order) {
             // any-order lanes postpone up to three siblings per level, each with its entry distance (8 B): a primary ray of the bunny
-            // never holds more than 16 entries (gpurun_out/r2_sweep1.log: 0 overflows of 2 M rays at 16, 65 of 4 Mi incoherent ones),
+            // never holds more than 16 entries (gpurun_out/r2_sweep1.log: 0 overflows of 2 M rays at 16, 65 of 4 Mi incoherent ones; 1 at 20, 0 at
+            // 22 - and ONE deferred ray costs a 20 us second launch, 2 % of that batch),
             // deep trees get up to 28 (a primary ray of the 2.5 M-leaf bunny field runs 4 % FASTER at 24 than at 32: occupancy, not
             // overflows, is what the cap costs); a lane that would need more defers its ray to the in-order kernel
             const uint32_t any_depth = ds->free_wide ? flat.free_depth : flat.wide_depth;
-            ds->any_cap = std::max<uint32_t>(4u, std::min<uint32_t>(3u * any_depth + 1u, any_depth <= 12 ? 20u : 28u));  // 28 x 1 KiB + 8 KiB of cold state: six blocks still fit one SM
+            ds->any_cap = std::max<uint32_t>(4u, std::min<uint32_t>(3u * any_depth + 1u, any_depth <= 12 ? 22u : 28u));  // six blocks per SM: 22 + 8 KiB stay inside the 196 KiB carve-out, 28 + 8 KiB inside 228
             if (const char* v = std::getenv("RTP_ANY_CAP")) ds->any_cap = static_cast<uint32_t>(std::max(4, std::min(48, std::atoi(v))));  // tests
             ds->any_stack_bytes = static_cast<size_t>(ds->any_cap) * 128 * sizeof(uint2) + kAnyColdBytes;  // the stacks, then the cold state
             if (ds->any_stack_bytes > 48u * 1024u) {  // deep trees: above the default limit of dynamic shared memory, every instantiation that is launched
