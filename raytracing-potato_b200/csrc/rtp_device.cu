@@ -1175,7 +1175,13 @@ __global__ void __launch_bounds__(128, OUT == OUT_TAIL ? 4 : kTraceBlocksPerSM) 
                                                                   TailArgs ta, DeferList index) {
     extern __shared__ __align__(16) uint32_t wide_stack[];  // [level][thread]
     if (n_dev) n = static_cast<size_t>(*n_dev);  // wavefront integrator: the batch size lives on the device
-    if (index.idx) n = static_cast<size_t>(*index.count);  // index mode: trace rays[index.idx[q]] for q < *index.count (deferred by trace_any_kernel)
+    if (index.idx) {
+        // index mode: trace rays[index.idx[q]] for q < *index.count (deferred by trace_any_kernel). This launch is a programmatic
+        // dependent of that kernel (launch_trace): its blocks may become resident while the last warps of trace_any_kernel still
+        // walk, and wait here until that grid has completed and its writes are visible.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        n = static_cast<size_t>(*index.count);
+    }
     if (OUT == OUT_TAIL) {
         if (n == 0 || n > ta.threshold) return;  // the trace/shade pair that follows handles this queue
         rays = ta.q.rays[ta.bounce & 1u];
@@ -1461,6 +1467,8 @@ template <bool COUNT, int OUT, bool GEN>
 __global__ void __launch_bounds__(128, RTP_ANY_BLOCKS) trace_any_kernel(DSceneView sc, const rtp_ray* __restrict__ rays, size_t n, void* __restrict__ out, Counters* counters,
                                                            WorkQueue* wq, Tuning tune, const unsigned long long* __restrict__ n_dev, DeferList defer, GenArgs gen) {
     extern __shared__ __align__(16) uint32_t any_stack[];
+    // the launch over the defer list (launch_trace) may be set up while this grid runs: it waits for this grid's completion itself
+    asm volatile("griddepcontrol.launch_dependents;");
     if (n_dev) n = static_cast<size_t>(*n_dev);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -2259,7 +2267,15 @@ static int launch_trace(DeviceScene* ds, const rtp_ray* d_rays, size_t n, void* 
             }
             // the deferred rays (normally none: the launch then finds an empty list and leaves at once), in the reference's order
             const dim3 g2(static_cast<unsigned>(std::min<size_t>(static_cast<size_t>(ds->inorder_blocks), want)));
-#define RTP_LAUNCH_DEFERRED(C, O) trace_persistent_kernel<C, O, false><<<g2, block, ds->inorder_stack_bytes, stream>>>(ds->view, d_rays, n, d_out, counters, wq, ds->tune, nullptr, ta, defer)
+            // programmatic dependent launch: the launch latency of this (normally empty) pass hides behind the tail of trace_any_kernel
+            cudaLaunchAttribute pdl;
+            pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl.val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t cfg2 = {};
+            cfg2.gridDim = g2; cfg2.blockDim = block; cfg2.dynamicSmemBytes = ds->inorder_stack_bytes; cfg2.stream = stream;
+            cfg2.attrs = &pdl; cfg2.numAttrs = 1;
+            const unsigned long long* const no_n_dev = nullptr;
+#define RTP_LAUNCH_DEFERRED(C, O) RTP_CUDA(cudaLaunchKernelEx(&cfg2, trace_persistent_kernel<C, O, false>, ds->view, d_rays, n, d_out, counters, wq, ds->tune, no_n_dev, ta, defer))
             if (out_mode == OUT_FULL) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_FULL); else RTP_LAUNCH_DEFERRED(false, OUT_FULL); }
             else if (out_mode == OUT_WAVE) { if (count) RTP_LAUNCH_DEFERRED(true, OUT_WAVE); else RTP_LAUNCH_DEFERRED(false, OUT_WAVE); }
             else { if (count) RTP_LAUNCH_DEFERRED(true, OUT_HIT); else RTP_LAUNCH_DEFERRED(false, OUT_HIT); }
